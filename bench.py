@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, sm_100a)
+  python bench.py --impl reference [...]                         the reference's CPU path (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU, weak scaling
+
+A step = one forward + backward of the integral L1 loss (soft-argmax + JointLocationLoss,
+/root/reference/common/nets/loss.py:13-52 and its autograd backward) over one batch of synthetic
+heatmaps: B=32 per GPU, J=18, D=H=W=64, fp32 -- the head output of BASELINE.json configs[1].
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "soft-argmax fwd+bwd joint-volumes/s"
+UNIT = "joint-volumes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--joints", type=int, default=18)
+    ap.add_argument("--depth", type=int, default=64)
+    ap.add_argument("--hw", type=int, default=64)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
+    ap.add_argument("--slices", type=int, default=8)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs_torch(B, J, D, H, W, device, dtype, seed):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    heat = torch.randn(B, J * D, H, W, device=device, generator=g, dtype=torch.float32).to(dtype)
+    gt = torch.rand(B, J, 3, device=device, generator=g) * torch.tensor([W, H, D], device=device, dtype=torch.float32)
+    vis = torch.ones(B, J, 1, device=device)
+    hd = torch.ones(B, 1, device=device)
+    return heat, gt, vis, hd
+
+
+def cpu_reference_leg(B, J, D, H, W, min_seconds, warmup=2, max_iters=50):
+    """The reference's CPU path (oracle/soft_argmax_ref.py: the same ATen calls as loss.py:13-52 + autograd),
+    all host threads, on a bounded sample of the workload.  Returns (volumes/s, cores, iters, seconds)."""
+    import torch
+    from oracle.soft_argmax_ref import ref_fwd_bwd
+    cores = torch.get_num_threads()
+    heat, gt, vis, hd = make_inputs_torch(B, J, D, H, W, "cpu", torch.float32, 0)
+    for _ in range(warmup):
+        ref_fwd_bwd(heat, gt, vis, hd)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        ref_fwd_bwd(heat, gt, vis, hd)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or n >= max_iters:
+            break
+    return B * J * n / dt, cores, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    B, J, D, W = args.batch, args.joints, args.depth, args.hw
+    sample_B = min(B, 8)
+    from oracle.soft_argmax_ref import ref_fwd_bwd
+    heat, gt, vis, hd = make_inputs_torch(sample_B, J, D, W, W, "cpu", torch.float32, 0)
+    for _ in range(max(1, min(args.warmup, 3))):
+        ref_fwd_bwd(heat, gt, vis, hd)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        ref_fwd_bwd(heat, gt, vis, hd)
+        done += 1
+        if time.perf_counter() - t0 > 120:      # keep the whole run within minutes on a slow host
+            break
+    dt = time.perf_counter() - t0
+    val = sample_B * J * done / dt
+    cores = torch.get_num_threads()
+    sample = "B=%d of the B=%d batch per step (J=%d, %dx%dx%d fp32), %d steps, torch CPU eager ops" % (sample_B, B, J, D, W, W, done)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / done * (B / sample_B), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "integral-L1 soft-argmax fwd+bwd, B=%d, J=%d, D=%d, H=W=%d, fp32" % (B, J, D, W)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import ihpr_b200
+    from ihpr_b200 import functional as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA sm_100 device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, J, D, W = args.batch, args.joints, args.depth, args.hw
+    H = W
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    es = 4 if args.dtype == "f32" else 2
+    R, N = B * J, D * H * W
+    ihpr_b200.set_variant(args.variant)
+    heat, gt, vis, hd = make_inputs_torch(B, J, D, H, W, dev, dtype, 1234 + rank)
+    heat.requires_grad_(True)
+    crit = ihpr_b200.JointLocationLoss()
+
+    def step():
+        heat.grad = None
+        loss = crit(heat, gt, vis, hd)
+        loss.backward()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = 0
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(K):
+        heat.grad = None
+        ev[i][0].record()
+        loss = crit(heat, gt, vis, hd)
+        launches += F.last_launch_count()
+        ev[i][1].record()
+        loss.backward()
+        launches += 1           # one backward kernel per step (ihpr_integral_l1_bwd)
+        ev[i][2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    if world > 1:
+        t = torch.tensor([total_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, fwd_ms, bwd_ms = t.tolist()
+    ms_per_step = total_ms / K
+    value = world * R / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step through the host-buffer C-ABI entry point, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hh = torch.empty(heat.shape, dtype=dtype, pin_memory=True)
+        hh.copy_(heat.detach())
+        out = {"grad": torch.empty(heat.shape, dtype=dtype, pin_memory=True), "loss": torch.empty(1).pin_memory(),
+               "coords": torch.empty(B, J, 3).pin_memory()}
+        gth, vish, hdh = gt.cpu().pin_memory(), vis.cpu().pin_memory(), hd.cpu().pin_memory()
+        ke = args.e2e_steps or min(K, 10)
+        for _ in range(2):
+            F.integral_l1_fwd_bwd_host(hh, gth, vish, hdh, device=local, slices=args.slices, out=out)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            F.integral_l1_fwd_bwd_host(hh, gth, vish, hdh, device=local, slices=args.slices, out=out)
+        e2e_s = (time.perf_counter() - t0) / ke
+        e2e_launch = F.last_launch_count()
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = t.item()
+        small_in = (R * 3 + R + B + 1) * 4
+        e2e = {"value": world * R / e2e_s, "unit": UNIT, "h2d_bytes_per_step": R * N * es + small_in,
+               "d2h_bytes_per_step": R * N * es + R * 3 * 4 + 4, "ms_per_step": e2e_s * 1e3, "steps": ke,
+               "launches_per_step": e2e_launch, "slices": args.slices,
+               "api": "ihpr_integral_l1_fwd_bwd_host (pinned host buffers, synchronous)"}
+        del hh, out
+        ihpr_b200._lib.lib().ihpr_host_release(local)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    bytes_fwd, bytes_bwd = R * N * es, 2 * R * N * es
+    dom = "bwd" if bwd_ms >= fwd_ms else "fwd"
+    dom_bytes, dom_ms = (bytes_bwd, bwd_ms) if dom == "bwd" else (bytes_fwd, fwd_ms)
+    roofline = {"bound": "hbm", "kernel": "bwd_ring_kernel (K2)" if dom == "bwd" else "fwd_ring_kernel (K1)",
+                "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms}
+    roofline["frac"] = roofline["achieved"] / peak
+    both = (bytes_fwd + bytes_bwd) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9
+    extra = {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": bytes_fwd / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": bytes_bwd / (bwd_ms * 1e-3) / 1e9,
+             "fwd_bwd_GBps": both, "fwd_bwd_frac_of_measured": both / peak, "fwd_bwd_frac_of_nominal_8TBps": both / 8000.0,
+             "step_GBps_incl_launch_gaps": (bytes_fwd + bytes_bwd) / (ms_per_step * 1e-3) / 1e9}
+
+    cpu = None
+    if not args.no_cpu:
+        sB = 4
+        v, cores, n, dt = cpu_reference_leg(sB, J, D, H, W, min_seconds=10.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "B=%d of the B=%d batch (J=%d, %dx%dx%d fp32), %d fwd+bwd iterations in %.1f s, torch CPU eager ops "
+                         "(oracle/soft_argmax_ref.py = reference loss.py:13-52 op for op), host has %d logical CPUs"
+                         % (sB, B, J, D, H, W, n, dt, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "integral-L1 soft-argmax fwd+bwd (JointLocationLoss + backward), B=%d per GPU, J=%d, D=%d, H=W=%d, %s heatmaps "
+                               "resident in HBM" % (B, J, D, W, args.dtype),
+                   "l2": "inputs %d MiB + gradients %d MiB per step >> 126 MB L2; no flush needed" % (R * N * es >> 20, R * N * es >> 20),
+                   "variant": ihpr_b200.get_variant(), "api": "ihpr_b200.JointLocationLoss()(heat, gt, vis, have_depth); loss.backward()"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": extra, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+/*
+ * ihpr_b200.h -- C-ABI of the B200-native integral-regression (3D soft-argmax) hot path.
+ *
+ * Every entry point replaces a Python call site of the reference (the reference has no FFI layer of
+ * its own: the seam is the three callables of common/nets/loss.py and main/model.py; INTEGRATION.md
+ * shows the ctypes binding a maintainer adds).  Citations are relative to /root/reference/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless the
+ *     function name ends in _host.
+ *   - heat is the head's output (B, J*D, H, W), NCHW-contiguous, channel c = j*D + d
+ *     (common/nets/loss.py:16,18).  Joint-volume r = b*J + j is the contiguous run of
+ *     N = D*H*W elements starting at r*N.  dtype: IHPR_F32 or IHPR_BF16.
+ *   - coords are (B, J, 3) fp32 in (x, y, z) order, 0-based voxel units (loss.py:28-32).
+ *   - stats are (B, J, 2) fp32: {m = max_i h_i, l = sum_i exp(h_i - m)}; logsumexp = m + ln l.
+ *     The backward recomputes the softmax from heat + stats; the softmax is never materialised.
+ *   - the caller owns every buffer, including the workspace (size from ihpr_workspace_bytes, must be
+ *     zero-filled ONCE before first use; the kernels leave it zeroed again).  A workspace must not be
+ *     shared by launches that may run concurrently (one per stream).
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
+ *     except the *_host entry point, which is synchronous by contract.
+ *   - return 0 on success, a negative IHPR_E* code otherwise; ihpr_last_error() gives the text
+ *     (thread-local).  No entry point ever falls back to a CPU implementation.
+ *   - NaN policy is the reference's: a row of all -inf gives NaN, +inf or NaN inputs propagate NaN
+ *     to that row's outputs.
+ *   - thread-safe: no global mutable state besides an immutable per-device attribute cache; the
+ *     reference calls its criterion from N Python threads, one per GPU
+ *     (common/nets/balanced_parallel.py:149-173).
+ */
+#ifndef IHPR_B200_H_
+#define IHPR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IHPR_VERSION 100            /* major*10000 + minor*100 + patch */
+
+#define IHPR_OK        0
+#define IHPR_EINVAL   -1            /* bad shape / null pointer / misaligned buffer / small workspace */
+#define IHPR_EARCH    -2            /* device is not sm_100 */
+#define IHPR_ECUDA    -3            /* CUDA runtime / launch failure; see ihpr_last_error() */
+
+#define IHPR_F32       0
+#define IHPR_BF16      1
+
+int         ihpr_version(void);
+const char *ihpr_last_error(void);
+
+/* Bytes of caller-owned, zero-initialised scratch the kernels need for this problem size. */
+size_t ihpr_workspace_bytes(int B, int J, int D, int H, int W);
+
+/* soft_argmax(heatmaps, joint_num) -> (B,J,3)            replaces common/nets/loss.py:13-34
+ * (called from main/test.py:65,72, main/main.py:57, main/mpii_s3d.py:70, main/up3d_s3d.py:67).
+ * stats may be NULL (inference, torch.no_grad path of main/test.py:53). */
+int ihpr_softargmax3d_fwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
+                          float *coords, float *stats,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* autograd backward of soft_argmax (implicit in the reference: loss.backward(), main/train.py:71):
+ * grad_heat[i] = p_i * sum_c grad_coords_c * (c(i) - coords_c), written in heat's dtype. */
+int ihpr_softargmax3d_bwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
+                          const float *coords, const float *stats, const float *grad_coords,
+                          void *grad_heat, void *stream);
+
+/* JointLocationLoss.forward(heatmap_out, gt_coord, gt_vis, gt_have_depth) -> scalar
+ *                                                         replaces common/nets/loss.py:36-52
+ * (called from main/train.py:67 through DataParallelCriterion, common/base.py:71).
+ * gt (B,J,3), vis (B,J,1), have_depth (B,1), all fp32.  Writes loss[0], coords and stats. */
+int ihpr_integral_l1_fwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
+                         const float *gt, const float *vis, const float *have_depth,
+                         float *loss, float *coords, float *stats,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* backward of the above: grad_out is a DEVICE pointer to the scalar d(objective)/d(loss)
+ * (autograd's incoming gradient; 1.0 for loss.backward()).  Fuses
+ * g_c = grad_out * sign(coord_c - gt_c) * vis * w_c / (3*B*J)   (loss.py:49-52)
+ * with the soft-argmax backward; writes grad_heat in heat's dtype. */
+int ihpr_integral_l1_bwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
+                         const float *coords, const float *stats,
+                         const float *gt, const float *vis, const float *have_depth,
+                         const float *grad_out, void *grad_heat, void *stream);
+
+/* One reference training step of the path with HOST buffers (what a CPU caller of
+ * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in
+ * `slices` batch slices pipelined over internal streams, runs forward + backward and copies
+ * loss / coords / grad_heat back.  Synchronous.  grad_heat_host may be NULL (loss only).
+ * Pinned host buffers are required for the copies to overlap; pageable ones still work. */
+int ihpr_integral_l1_fwd_bwd_host(const void *heat_host, int dtype, int B, int J, int D, int H, int W,
+                                  const float *gt_host, const float *vis_host, const float *have_depth_host,
+                                  float grad_out, float *loss_host, float *coords_host,
+                                  void *grad_heat_host, int device, int slices);
+
+/* Frees the device buffers / streams the *_host entry point caches for `device`. */
+int ihpr_host_release(int device);
+
+/* Tuning / introspection (does not change results): kernel variant 0 = auto,
+ * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads. */
+int ihpr_set_variant(int variant);
+int ihpr_get_variant(void);
+/* Number of kernels the LAST call on this thread launched (for bench.py's gpu_launches). */
+int ihpr_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IHPR_B200_H_ */

@@ -1,0 +1,16 @@
+"""ihpr_b200 -- B200-native (sm_100a) integral-regression hot path.
+
+Drop-in for the reference's ``common/nets/loss.py`` callables (``soft_argmax``,
+``JointLocationLoss``) backed by hand-written CUDA kernels behind a C-ABI library
+(``include/ihpr_b200.h``).  There is no CPU fallback: without the built library or without an
+sm_100 device every op raises.
+"""
+from .functional import (soft_argmax, integral_l1_loss, integral_l1_fwd_bwd_host, last_launch_count,  # noqa: F401
+                         set_variant, get_variant)
+from .nets.loss import JointLocationLoss, JointMSELoss  # noqa: F401
+from .dropin import install_dropin  # noqa: F401
+from ._lib import IhprError, library_path, version  # noqa: F401
+
+__all__ = ["soft_argmax", "integral_l1_loss", "integral_l1_fwd_bwd_host", "JointLocationLoss", "JointMSELoss",
+           "install_dropin", "IhprError", "library_path", "version", "set_variant", "get_variant",
+           "last_launch_count"]

@@ -1,0 +1,329 @@
+// c_api.cu -- the C-ABI boundary declared in include/ihpr_b200.h: argument validation, workspace
+// carving, variant selection, launches on the caller's stream, error reporting.  No torch types,
+// no CPU fallback: a device that is not sm_100 is refused with IHPR_EARCH.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/ihpr_b200.h"
+#include "ihpr_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+std::atomic<int> g_variant{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define IHPR_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return fail(IHPR_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int max_slots(int D, int H, int W) {
+    const uint64_t N = (uint64_t)D * H * W;
+    uint64_t nch = (N + ihpr::kMinChunkElems - 1) / ihpr::kMinChunkElems;
+    if (nch > (uint64_t)ihpr::kGridCap) nch = ihpr::kGridCap;
+    return (int)nch;
+}
+
+struct WsLayout {
+    size_t off_row_count, off_done, off_row_loss, off_partials, total;
+};
+WsLayout ws_layout(int B, int J, int D, int H, int W) {
+    const size_t R = (size_t)B * J;
+    WsLayout l;
+    l.off_row_count = 0;
+    l.off_done = R * sizeof(int);
+    l.off_row_loss = align_up(l.off_done + sizeof(int), 256);
+    l.off_partials = align_up(l.off_row_loss + R * sizeof(float), 256);
+    l.total = align_up(l.off_partials + R * (size_t)max_slots(D, H, W) * 8 * sizeof(float), 256);
+    return l;
+}
+
+int check_shape(int B, int J, int D, int H, int W, int dtype) {
+    if (B <= 0 || J <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(IHPR_EINVAL, "non-positive dimension B=%d J=%d D=%d H=%d W=%d", B, J, D, H, W);
+    if (dtype != IHPR_F32 && dtype != IHPR_BF16) return fail(IHPR_EINVAL, "dtype %d is neither IHPR_F32 nor IHPR_BF16", dtype);
+    const uint64_t N = (uint64_t)D * H * W;
+    if (N > (1ull << 30) || W >= (1 << 21) || H >= (1 << 23) || D >= (1 << 23)) return fail(IHPR_EINVAL, "joint-volume too large (D*H*W = %llu)", (unsigned long long)N);
+    if ((uint64_t)B * J > (1ull << 30)) return fail(IHPR_EINVAL, "too many joint-volumes");
+    return IHPR_OK;
+}
+
+// device of the pointer must be the current device and an sm_100 part
+int check_device(const void* ptr, int* num_sms) {
+    int dev = -1;
+    IHPR_CUDA(cudaGetDevice(&dev));
+    cudaPointerAttributes at;
+    IHPR_CUDA(cudaPointerGetAttributes(&at, ptr));
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return fail(IHPR_EINVAL, "heat is not a device pointer");
+    if (at.device != dev) return fail(IHPR_EINVAL, "heat lives on device %d but the current device is %d", at.device, dev);
+    int major = 0, minor = 0;
+    IHPR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    IHPR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10 || minor != 0) return fail(IHPR_EARCH, "device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+    IHPR_CUDA(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev));
+    return IHPR_OK;
+}
+
+bool vec_ok(const void* a, const void* b, int dtype, int D, int H, int W) {
+    const uint64_t N = (uint64_t)D * H * W;
+    if (W % 4 != 0) return false;
+    if (dtype == IHPR_BF16 && N % 8 != 0) return false;
+    if (((uintptr_t)a | (uintptr_t)b) & 15) return false;
+    return true;
+}
+
+int fwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* gt, const float* vis, const float* hd, float* loss,
+               float* coords, float* stats, void* ws, size_t ws_bytes, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, J, D, H, W, dtype);
+    if (rc) return rc;
+    if (!heat || !coords || !ws) return fail(IHPR_EINVAL, "null heat / coords / workspace");
+    if (gt && (!vis || !hd || !loss)) return fail(IHPR_EINVAL, "gt given but vis / have_depth / loss is null");
+    const WsLayout l = ws_layout(B, J, D, H, W);
+    if (ws_bytes < l.total) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", ws_bytes, l.total);
+    if ((uintptr_t)ws & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    int num_sms = 0;
+    rc = check_device(heat, &num_sms);
+    if (rc) return rc;
+
+    const bool v = vec_ok(heat, nullptr, dtype, D, H, W);
+    const int variant = g_variant.load(std::memory_order_relaxed);
+    ihpr::FwdParams p;
+    p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
+    p.heat = heat; p.coords = coords; p.stats = stats;
+    p.gt = gt; p.vis = vis; p.have_depth = hd; p.loss = loss;
+    char* w8 = static_cast<char*>(ws);
+    p.row_count = reinterpret_cast<int*>(w8 + l.off_row_count);
+    p.done_rows = reinterpret_cast<int*>(w8 + l.off_done);
+    p.row_loss = reinterpret_cast<float*>(w8 + l.off_row_loss);
+    p.partials = reinterpret_cast<float*>(w8 + l.off_partials);
+    p.maxslots = max_slots(D, H, W);
+    ihpr::launch_fwd(p, dtype, v, variant, num_sms, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+int bwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* coords, const float* stats, const float* grad_coords,
+               const float* gt, const float* vis, const float* hd, const float* grad_out, float loss_scale, void* grad_heat, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, J, D, H, W, dtype);
+    if (rc) return rc;
+    if (!heat || !coords || !stats || !grad_heat) return fail(IHPR_EINVAL, "null heat / coords / stats / grad_heat");
+    if (!grad_coords && (!gt || !vis || !hd || !grad_out)) return fail(IHPR_EINVAL, "fused-loss backward needs gt, vis, have_depth and grad_out");
+    int num_sms = 0;
+    rc = check_device(heat, &num_sms);
+    if (rc) return rc;
+    const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
+    const int variant = g_variant.load(std::memory_order_relaxed);
+    ihpr::BwdParams p;
+    p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
+    p.heat = heat; p.grad_heat = grad_heat; p.coords = coords; p.stats = stats;
+    p.grad_coords = grad_coords; p.gt = gt; p.vis = vis; p.have_depth = hd; p.grad_out = grad_out;
+    p.loss_scale = loss_scale;
+    ihpr::launch_bwd(p, dtype, v, variant, num_sms, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+// ---- host-buffer entry point: per-device cache of device buffers + copy streams ----------------
+struct HostCtx {
+    int device = -1;
+    size_t cap_heat = 0, cap_small = 0, cap_ws = 0;
+    void *d_heat = nullptr, *d_grad = nullptr, *d_ws = nullptr;
+    float* d_small = nullptr;       // gt, vis, hd, coords, stats, loss, grad_out
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+};
+std::mutex g_host_mu;
+HostCtx g_host[16];
+
+__global__ void loss_from_coords_kernel(const float* coords, const float* gt, const float* vis, const float* hd, int R, int J, float* loss) {
+    // loss.py:49-52 on final coords: one warp, index-ordered -> bit-reproducible
+    float s = 0.f;
+    for (int r = threadIdx.x; r < R; r += 32) {
+        const float v = vis[r], d = hd[r / J];
+        s += (fabsf(coords[3 * r] - gt[3 * r]) * v + fabsf(coords[3 * r + 1] - gt[3 * r + 1]) * v + fabsf(coords[3 * r + 2] - gt[3 * r + 2]) * v * d) / 3.f;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) loss[0] = s / (float)R;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ihpr_version(void) { return IHPR_VERSION; }
+const char* ihpr_last_error(void) { return g_err; }
+int ihpr_set_variant(int variant) { g_variant.store(variant); return IHPR_OK; }
+int ihpr_get_variant(void) { return g_variant.load(); }
+int ihpr_last_launch_count(void) { return g_launches; }
+
+size_t ihpr_workspace_bytes(int B, int J, int D, int H, int W) {
+    if (B <= 0 || J <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return ws_layout(B, J, D, H, W).total;
+}
+
+int ihpr_softargmax3d_fwd(const void* heat, int dtype, int B, int J, int D, int H, int W, float* coords, float* stats, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    return fwd_common(heat, dtype, B, J, D, H, W, nullptr, nullptr, nullptr, nullptr, coords, stats, workspace, workspace_bytes, stream);
+}
+
+int ihpr_softargmax3d_bwd(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* coords, const float* stats,
+                          const float* grad_coords, void* grad_heat, void* stream) {
+    if (!grad_coords) return fail(IHPR_EINVAL, "null grad_coords");
+    return bwd_common(heat, dtype, B, J, D, H, W, coords, stats, grad_coords, nullptr, nullptr, nullptr, nullptr, 0.f, grad_heat, stream);
+}
+
+int ihpr_integral_l1_fwd(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* gt, const float* vis, const float* have_depth,
+                         float* loss, float* coords, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!gt || !vis || !have_depth || !loss) return fail(IHPR_EINVAL, "null gt / vis / have_depth / loss");
+    return fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
+}
+
+int ihpr_integral_l1_bwd(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* coords, const float* stats, const float* gt,
+                         const float* vis, const float* have_depth, const float* grad_out, void* grad_heat, void* stream) {
+    const float scale = 1.0f / (3.0f * (float)B * (float)J);
+    return bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, grad_out, scale, grad_heat, stream);
+}
+
+int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
+                                  const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
+                                  int device, int slices) {
+    g_launches = 0;
+    int rc = check_shape(B, J, D, H, W, dtype);
+    if (rc) return rc;
+    if (!heat_host || !gt_host || !vis_host || !have_depth_host || !loss_host) return fail(IHPR_EINVAL, "null host buffer");
+    if (device < 0 || device >= 16) return fail(IHPR_EINVAL, "device %d out of range", device);
+    if (slices < 1) slices = 1;
+    if (slices > B) slices = B;
+
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    int prev = -1;
+    IHPR_CUDA(cudaGetDevice(&prev));
+    IHPR_CUDA(cudaSetDevice(device));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+
+    HostCtx& c = g_host[device];
+    const size_t es = dtype == IHPR_F32 ? 4 : 2;
+    const size_t R = (size_t)B * J, N = (size_t)D * H * W;
+    const size_t heat_bytes = R * N * es;
+    const size_t n_small = R * 3 + R + B + R * 3 + R * 2 + 2;        // gt, vis, hd, coords, stats, loss, grad_out
+    const size_t ws_slice = ihpr_workspace_bytes((B + slices - 1) / slices, J, D, H, W);
+    if (c.device != device) {
+        c.device = device;
+        for (auto& s : c.streams) IHPR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        IHPR_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    }
+    if (c.cap_heat < heat_bytes) {
+        if (c.d_heat) cudaFree(c.d_heat);
+        if (c.d_grad) cudaFree(c.d_grad);
+        c.d_heat = c.d_grad = nullptr; c.cap_heat = 0;
+        IHPR_CUDA(cudaMalloc(&c.d_heat, heat_bytes));
+        IHPR_CUDA(cudaMalloc(&c.d_grad, heat_bytes));
+        c.cap_heat = heat_bytes;
+    }
+    if (c.cap_small < n_small) {
+        if (c.d_small) cudaFree(c.d_small);
+        c.d_small = nullptr; c.cap_small = 0;
+        IHPR_CUDA(cudaMalloc(&c.d_small, n_small * sizeof(float)));
+        c.cap_small = n_small;
+    }
+    if (c.cap_ws < 3 * ws_slice) {
+        if (c.d_ws) cudaFree(c.d_ws);
+        c.d_ws = nullptr; c.cap_ws = 0;
+        IHPR_CUDA(cudaMalloc(&c.d_ws, 3 * ws_slice));
+        c.cap_ws = 3 * ws_slice;
+    }
+    IHPR_CUDA(cudaMemsetAsync(c.d_ws, 0, 3 * ws_slice, c.streams[0]));
+    float* d_gt = c.d_small;
+    float* d_vis = d_gt + R * 3;
+    float* d_hd = d_vis + R;
+    float* d_coords = d_hd + B;
+    float* d_stats = d_coords + R * 3;
+    float* d_loss = d_stats + R * 2;
+    float* d_go = d_loss + 1;
+
+    // targets first, on stream 0; the other streams wait for them
+    IHPR_CUDA(cudaMemcpyAsync(d_gt, gt_host, R * 3 * sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
+    IHPR_CUDA(cudaMemcpyAsync(d_vis, vis_host, R * sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
+    IHPR_CUDA(cudaMemcpyAsync(d_hd, have_depth_host, B * sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
+    IHPR_CUDA(cudaMemcpyAsync(d_go, &grad_out, sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
+    IHPR_CUDA(cudaEventRecord(c.ready, c.streams[0]));
+    IHPR_CUDA(cudaStreamWaitEvent(c.streams[1], c.ready, 0));
+    IHPR_CUDA(cudaStreamWaitEvent(c.streams[2], c.ready, 0));
+
+    const float scale = 1.0f / (3.0f * (float)B * (float)J);
+    const int variant = g_variant.load(std::memory_order_relaxed);
+    int num_sms = 0;
+    rc = check_device(c.d_heat, &num_sms);
+    if (rc) return rc;
+    int launches = 0;
+    for (int i = 0; i < slices; ++i) {
+        const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
+        const int Bs = b1 - b0;
+        if (Bs <= 0) continue;
+        cudaStream_t st = c.streams[i % 3];
+        const size_t r0 = (size_t)b0 * J;
+        const size_t off = r0 * N * es, bytes = (size_t)Bs * J * N * es;
+        char* dh = static_cast<char*>(c.d_heat) + off;
+        char* dg = static_cast<char*>(c.d_grad) + off;
+        IHPR_CUDA(cudaMemcpyAsync(dh, static_cast<const char*>(heat_host) + off, bytes, cudaMemcpyHostToDevice, st));
+        rc = ihpr_softargmax3d_fwd(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, static_cast<char*>(c.d_ws) + (i % 3) * ws_slice,
+                                   ws_slice, st);
+        if (rc) return rc;
+        ++launches;
+        if (grad_heat_host) {
+            rc = bwd_common(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, nullptr, d_gt + r0 * 3, d_vis + r0, d_hd + b0, d_go, scale,
+                            dg, st);
+            if (rc) return rc;
+            ++launches;
+            IHPR_CUDA(cudaMemcpyAsync(static_cast<char*>(grad_heat_host) + off, dg, bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (auto& s : c.streams) IHPR_CUDA(cudaStreamSynchronize(s));
+    loss_from_coords_kernel<<<1, 32, 0, c.streams[0]>>>(d_coords, d_gt, d_vis, d_hd, (int)R, J, d_loss);
+    ++launches;
+    IHPR_CUDA(cudaGetLastError());
+    IHPR_CUDA(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, c.streams[0]));
+    if (coords_host) IHPR_CUDA(cudaMemcpyAsync(coords_host, d_coords, R * 3 * sizeof(float), cudaMemcpyDeviceToHost, c.streams[0]));
+    IHPR_CUDA(cudaStreamSynchronize(c.streams[0]));
+    g_launches = launches;
+    return IHPR_OK;
+}
+
+int ihpr_host_release(int device) {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    if (device < 0 || device >= 16) return fail(IHPR_EINVAL, "device %d out of range", device);
+    HostCtx& c = g_host[device];
+    if (c.device != device) return IHPR_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    if (c.d_heat) cudaFree(c.d_heat);
+    if (c.d_grad) cudaFree(c.d_grad);
+    if (c.d_ws) cudaFree(c.d_ws);
+    if (c.d_small) cudaFree(c.d_small);
+    for (auto& s : c.streams) if (s) cudaStreamDestroy(s);
+    if (c.ready) cudaEventDestroy(c.ready);
+    c = HostCtx();
+    cudaSetDevice(prev);
+    return IHPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+"""Host-side operators of the hot path: torch tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory, the current stream, autograd bookkeeping); all arithmetic
+runs in lib/libihpr_b200.so.  Semantics follow /root/reference/common/nets/loss.py:13-52.
+"""
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import IHPR_BF16, IHPR_F32, IhprError, check, lib
+
+_ws_lock = threading.Lock()
+_ws_cache = {}      # (device index, stream handle) -> zero-initialised uint8 workspace
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return IHPR_F32
+    if t.dtype == torch.bfloat16:
+        return IHPR_BF16
+    raise TypeError("ihpr_b200 kernels take float32 or bfloat16 heatmaps, got %s" % t.dtype)
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise IhprError("ihpr_b200: %s is on %s; this path runs on a CUDA sm_100 device only "
+                        "(there is no CPU fallback)" % (name, t.device))
+
+
+def _shape(heat, joint_num):
+    if heat.dim() != 4:
+        raise ValueError("heatmaps must be (B, J*D, H, W), got %s" % (tuple(heat.shape),))
+    B, C, H, W = heat.shape
+    if joint_num <= 0 or C % joint_num != 0:
+        raise ValueError("channel count %d is not a multiple of joint_num %d" % (C, joint_num))
+    return B, C // joint_num, H, W
+
+
+def _workspace(dev, stream, nbytes):
+    key = (dev.index, stream)
+    with _ws_lock:
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
+            _ws_cache[key] = ws
+    return ws
+
+
+def _f32(t, dev, shape, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.device != dev:
+        raise IhprError("%s is on %s but the heatmaps are on %s" % (name, t.device, dev))
+    t = t.detach()
+    if t.numel() != shape[0] * shape[1] * (shape[2] if len(shape) > 2 else 1):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), shape))
+    return t.to(torch.float32).contiguous()
+
+
+def _fwd(heat, joint_num, targets=None):
+    """heat: contiguous cuda f32/bf16.  Returns (coords, stats, loss-or-None)."""
+    B, D, H, W = _shape(heat, joint_num)
+    dev = heat.device
+    L = lib()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nbytes = L.ihpr_workspace_bytes(B, joint_num, D, H, W)
+        ws = _workspace(dev, stream, nbytes)
+        coords = torch.empty((B, joint_num, 3), dtype=torch.float32, device=dev)
+        stats = torch.empty((B, joint_num, 2), dtype=torch.float32, device=dev)
+        if targets is None:
+            check(L.ihpr_softargmax3d_fwd(heat.data_ptr(), _dtype_code(heat), B, joint_num, D, H, W,
+                                          coords.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+            return coords, stats, None
+        gt, vis, hd = targets
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        check(L.ihpr_integral_l1_fwd(heat.data_ptr(), _dtype_code(heat), B, joint_num, D, H, W,
+                                     gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), loss.data_ptr(),
+                                     coords.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        return coords, stats, loss
+
+
+class _SoftArgmax3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, heat, joint_num):
+        heat = heat.contiguous()
+        coords, stats, _ = _fwd(heat, joint_num)
+        ctx.joint_num = joint_num
+        ctx.save_for_backward(heat, coords, stats)      # heat is the conv output autograd keeps anyway; no softmax saved
+        return coords
+
+    @staticmethod
+    def backward(ctx, grad_coords):
+        heat, coords, stats = ctx.saved_tensors
+        J = ctx.joint_num
+        B, D, H, W = _shape(heat, J)
+        g = grad_coords.to(torch.float32).contiguous()
+        grad_heat = torch.empty_like(heat)
+        with torch.cuda.device(heat.device):
+            stream = torch.cuda.current_stream(heat.device).cuda_stream
+            check(lib().ihpr_softargmax3d_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
+                                              stats.data_ptr(), g.data_ptr(), grad_heat.data_ptr(), stream))
+        return grad_heat, None
+
+
+class _IntegralL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, heat, gt, vis, hd):
+        heat = heat.contiguous()
+        J = gt.shape[1]
+        coords, stats, loss = _fwd(heat, J, (gt, vis, hd))
+        ctx.joint_num = J
+        ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
+        ctx.mark_non_differentiable(coords)
+        return loss, coords
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_coords):
+        heat, coords, stats, gt, vis, hd = ctx.saved_tensors
+        J = ctx.joint_num
+        B, D, H, W = _shape(heat, J)
+        go = grad_loss.to(torch.float32).contiguous()
+        grad_heat = torch.empty_like(heat)
+        with torch.cuda.device(heat.device):
+            stream = torch.cuda.current_stream(heat.device).cuda_stream
+            check(lib().ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
+                                             stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
+                                             go.data_ptr(), grad_heat.data_ptr(), stream))
+        return grad_heat, None, None, None
+
+
+def _normalise(heat):
+    # fp16 / fp64 heatmaps are computed in fp32 (the cast is differentiable torch plumbing)
+    if heat.dtype not in (torch.float32, torch.bfloat16):
+        if not heat.is_floating_point():
+            raise TypeError("heatmaps must be floating point, got %s" % heat.dtype)
+        return heat.to(torch.float32)
+    return heat
+
+
+def soft_argmax(heatmaps, joint_num):
+    """(B, J*D, H, W) heatmaps -> (B, J, 3) expected (x, y, z) voxel coordinates, fp32.
+    Same contract as /root/reference/common/nets/loss.py:13-34; D is inferred as C // joint_num."""
+    assert isinstance(heatmaps, torch.Tensor)                    # loss.py:14
+    _require_cuda(heatmaps, "heatmaps")
+    _shape(heatmaps, joint_num)
+    return _SoftArgmax3D.apply(_normalise(heatmaps), int(joint_num))
+
+
+def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords=False):
+    """Fused soft-argmax + L1 coordinate loss (loss.py:36-52): one launch forward, one backward."""
+    _require_cuda(heatmap_out, "heatmap_out")
+    if gt_coord.dim() != 3 or gt_coord.shape[2] != 3:
+        raise ValueError("gt_coord must be (B, J, 3), got %s" % (tuple(gt_coord.shape),))
+    B, J = gt_coord.shape[0], gt_coord.shape[1]
+    _shape(heatmap_out, J)
+    if heatmap_out.shape[0] != B:
+        raise ValueError("batch mismatch: heatmaps %d vs gt_coord %d" % (heatmap_out.shape[0], B))
+    dev = heatmap_out.device
+    gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
+    vis = _f32(gt_vis, dev, (B, J), "gt_vis")
+    hd = _f32(gt_have_depth, dev, (B, 1), "gt_have_depth")
+    loss, coords = _IntegralL1.apply(_normalise(heatmap_out), gt, vis, hd)
+    return (loss, coords) if return_coords else loss
+
+
+def integral_l1_fwd_bwd_host(heat, gt_coord, gt_vis, gt_have_depth, grad_out=1.0, want_grad=True, device=0, slices=8,
+                             out=None):
+    """Host-buffer step (ihpr_integral_l1_fwd_bwd_host): CPU tensors in, CPU tensors out, the copies
+    are inside.  `heat` / `out` should be pinned for the copies to overlap with the kernels."""
+    for t, n in ((heat, "heat"), (gt_coord, "gt_coord"), (gt_vis, "gt_vis"), (gt_have_depth, "gt_have_depth")):
+        if t.is_cuda:
+            raise ValueError("%s must be a host tensor for the *_host entry point" % n)
+    heat = heat.contiguous()
+    B, J = gt_coord.shape[0], gt_coord.shape[1]
+    _, D, H, W = _shape(heat, J)
+    gt = gt_coord.to(torch.float32).contiguous()
+    vis = gt_vis.to(torch.float32).contiguous()
+    hd = gt_have_depth.to(torch.float32).contiguous()
+    if out is None:
+        out = {}
+    loss = out.get("loss")
+    if loss is None:
+        loss = out["loss"] = torch.empty(1, dtype=torch.float32)
+    coords = out.get("coords")
+    if coords is None:
+        coords = out["coords"] = torch.empty((B, J, 3), dtype=torch.float32)
+    grad = None
+    if want_grad:
+        grad = out.get("grad")
+        if grad is None:
+            grad = out["grad"] = torch.empty_like(heat)
+    check(lib().ihpr_integral_l1_fwd_bwd_host(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, gt.data_ptr(),
+                                              vis.data_ptr(), hd.data_ptr(), float(grad_out), loss.data_ptr(),
+                                              coords.data_ptr(), grad.data_ptr() if grad is not None else None,
+                                              int(device), int(slices)))
+    return loss, coords, grad
+
+
+def last_launch_count():
+    return lib().ihpr_last_launch_count()
+
+
+def set_variant(v):
+    check(lib().ihpr_set_variant(int(v)))
+
+
+def get_variant():
+    return lib().ihpr_get_variant()

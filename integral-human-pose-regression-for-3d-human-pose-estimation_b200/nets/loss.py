@@ -1,0 +1,80 @@
+"""Drop-in for /root/reference/common/nets/loss.py -- same names, arguments and error behaviour.
+
+``soft_argmax`` (loss.py:13-34) and ``JointLocationLoss`` (loss.py:36-52) dispatch to the sm_100a
+kernels; ``JointMSELoss`` (loss.py:55-84, the direct-regression baseline's criterion, off the hot
+path) is plain torch so ``common/base.py:207`` keeps importing.
+
+Differences a caller can observe: the volume shape is inferred from the tensor (C // joint_num,
+H, W) instead of read from the global ``cfg`` (loss.py:16,18) -- when a ``config`` module with
+``cfg`` is loaded it is cross-checked; CPU tensors raise (the reference also only runs on CUDA,
+loss.py:24-26).
+"""
+import sys
+
+import torch
+import torch.nn as nn
+
+from ..functional import integral_l1_loss
+from ..functional import soft_argmax as _soft_argmax
+
+
+def _assert_no_grad(tensor):                                             # loss.py:8-11
+    assert not tensor.requires_grad, \
+        "nn criterions don't compute the gradient w.r.t. targets - please " \
+        "mark these tensors as not requiring gradients"
+
+
+def _check_cfg(heatmaps, joint_num):
+    cfg_mod = sys.modules.get("config")
+    cfg = getattr(cfg_mod, "cfg", None)
+    if cfg is None or not hasattr(cfg, "depth_dim") or not hasattr(cfg, "output_shape"):
+        return
+    C, H, W = heatmaps.shape[1], heatmaps.shape[2], heatmaps.shape[3]
+    if C != joint_num * cfg.depth_dim or (H, W) != tuple(cfg.output_shape):
+        raise ValueError("heatmaps %s disagree with cfg (depth_dim=%s, output_shape=%s, joint_num=%d)"
+                         % (tuple(heatmaps.shape), cfg.depth_dim, cfg.output_shape, joint_num))
+
+
+def soft_argmax(heatmaps, joint_num):
+    assert isinstance(heatmaps, torch.Tensor)                            # loss.py:14
+    _check_cfg(heatmaps, joint_num)
+    return _soft_argmax(heatmaps, joint_num)
+
+
+class JointLocationLoss(nn.Module):
+    def __init__(self):
+        super(JointLocationLoss, self).__init__()
+
+    def forward(self, heatmap_out, gt_coord, gt_vis, gt_have_depth):
+        joint_num = gt_coord.shape[1]                                    # loss.py:42
+        _assert_no_grad(gt_coord)                                        # loss.py:45-47
+        _assert_no_grad(gt_vis)
+        _assert_no_grad(gt_have_depth)
+        _check_cfg(heatmap_out, joint_num)
+        return integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth)
+
+
+class JointMSELoss(nn.Module):
+    """loss.py:55-84 (baseline regression criterion; not on the accelerated path)."""
+
+    def __init__(self):
+        super(JointMSELoss, self).__init__()
+        self.criterion = nn.MSELoss(reduction="mean")
+        self.use_target_weight = True
+
+    def forward(self, output, target, target_weight):
+        batch_size = target.size(0)
+        num_joints = target.size(1)
+        _assert_no_grad(target)
+        _assert_no_grad(target_weight)
+        coords_pred = output.reshape((batch_size, num_joints, -1)).split(1, 1)
+        coords_gt = target.reshape((batch_size, num_joints, -1)).split(1, 1)
+        loss = 0
+        for idx in range(num_joints):
+            coord_pred = coords_pred[idx].squeeze()
+            coord_gt = coords_gt[idx].squeeze()
+            if self.use_target_weight:
+                loss += 0.5 * self.criterion(coord_pred.mul(target_weight[:, idx]), coord_gt.mul(target_weight[:, idx]))
+            else:
+                loss += 0.5 * self.criterion(coord_pred, coord_gt)
+        return loss / num_joints

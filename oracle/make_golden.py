@@ -1,0 +1,87 @@
+"""oracle/make_golden.py -- produces tests/golden/*.npz by EXECUTING THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+
+For every case the unmodified reference ``soft_argmax`` + ``JointLocationLoss``
+(/root/reference/common/nets/loss.py:13-52, loaded by oracle/load_reference.py) is run forward and
+backward in fp32 (what the GPU kernels are compared with) and again in fp64 (the reference's own
+ops on double input: the "truth" column).  While doing so the two oracle restatements are pinned:
+oracle/soft_argmax_ref.py must be bit-identical to the reference in fp32, oracle/truth64.c must
+agree with the reference-in-fp64 to 1e-9.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import inputs, truth                     # noqa: E402
+from oracle.load_reference import Reference          # noqa: E402
+from oracle.soft_argmax_ref import ref_fwd_bwd       # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+GRAD_STRIDE = 61          # big cases keep every 61st gradient element (+ checksums) to stay small
+
+# name, dist, B, J, D, H, W, seed, vis_mode, hd_mode, keep_full
+CASES = [
+    ("randn1_b2j3_d8h8w8",      "randn1", 2, 3, 8, 8, 8, 1, "ones", "ones", True),
+    ("randn3_b1j17_d16h16w16",  "randn3", 1, 17, 16, 16, 16, 2, "ones", "ones", True),
+    ("init_b2j18_d8h16w12",     "init",   2, 18, 8, 16, 12, 3, "ones", "ones", True),
+    ("odd_b1j2_d5h7w9",         "randn1", 1, 2, 5, 7, 9, 4, "ones", "ones", True),
+    ("blobs_b1j4_d16h16w16",    "blobs",  1, 4, 16, 16, 16, 5, "ones", "ones", True),
+    ("large_b1j2_d8h8w8",       "large",  1, 2, 8, 8, 8, 6, "ones", "ones", True),
+    ("shifted_b1j2_d8h8w8",     "shifted", 1, 2, 8, 8, 8, 7, "ones", "ones", True),
+    ("mask_b3j5_d8h8w8",        "randn3", 3, 5, 8, 8, 8, 8, "rand", "alt", True),
+    ("nodepth_b2j16_d8h8w8",    "randn1", 2, 16, 8, 8, 8, 9, "rand", "zeros", True),
+    ("full_b1j2_d64h64w64",     "randn1", 1, 2, 64, 64, 64, 10, "ones", "ones", False),
+    ("fullblobs_b1j2_d64h64w64", "blobs", 1, 2, 64, 64, 64, 11, "ones", "ones", False),
+    ("d32_b2j17_d32h64w64",     "randn3", 2, 17, 32, 64, 64, 12, "rand", "alt", False),
+]
+
+
+def main():
+    ref = Reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(1)        # fixed summation order for the committed fp32 numbers
+    for name, dist, B, J, D, H, W, seed, vis_mode, hd_mode, keep_full in CASES:
+        heat = inputs.make_heat(dist, B, J, D, H, W, seed)
+        gt, vis, hd = inputs.make_targets(B, J, D, H, W, seed, vis_mode, hd_mode)
+        th, tgt, tvis, thd = (torch.from_numpy(a) for a in (heat, gt, vis, hd))
+
+        loss32, coords32, grad32 = ref.fwd_bwd(th, tgt, tvis, thd)
+        loss64, coords64, grad64 = ref.fwd_bwd(th.double(), tgt.double(), tvis.double(), thd.double())
+
+        # pin the torch restatement: identical ATen sequence -> bit-identical
+        l2, c2, g2 = ref_fwd_bwd(th, tgt, tvis, thd)
+        assert torch.equal(l2, loss32) and torch.equal(c2, coords32) and torch.equal(g2, grad32), name
+        # pin the fp64 C restatement against the reference run in fp64
+        lo, co, go = truth.fwd_bwd_f64(heat, gt, vis, hd)
+        assert abs(lo - loss64.item()) <= 1e-9 * max(1.0, abs(loss64.item())), name
+        assert np.abs(co - coords64.numpy()).max() <= 1e-9 * max(D, H, W), name
+        gmax = np.abs(grad64.numpy()).max()
+        assert np.abs(go - grad64.numpy()).max() <= 1e-9 * max(gmax, 1e-30), (name, np.abs(go - grad64.numpy()).max(), gmax)
+
+        out = dict(dist=dist, B=B, J=J, D=D, H=H, W=W, seed=seed, vis_mode=vis_mode, hd_mode=hd_mode,
+                   gt=gt, vis=vis, have_depth=hd,
+                   ref32_loss=np.float32(loss32.item()), ref32_coords=coords32.numpy(),
+                   ref64_loss=np.float64(loss64.item()), ref64_coords=coords64.numpy(),
+                   heat_sha=np.frombuffer(__import__("hashlib").sha256(heat.tobytes()).digest(), dtype=np.uint8),
+                   torch_version=str(torch.__version__))
+        g32 = grad32.numpy().reshape(-1); g64 = grad64.numpy().reshape(-1)
+        if keep_full:
+            out.update(heat=heat, ref32_grad=g32.reshape(heat.shape), ref64_grad=g64.reshape(heat.shape))
+        else:
+            out.update(grad_stride=GRAD_STRIDE, ref32_grad_sub=g32[::GRAD_STRIDE].copy(),
+                       ref64_grad_sub=g64[::GRAD_STRIDE].copy(),
+                       ref64_grad_abssum=np.float64(np.abs(g64).sum()), ref64_grad_max=np.float64(gmax))
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        err_c = np.abs(coords32.numpy() - coords64.numpy()).max()
+        err_g = np.abs(g32 - g64).max() / max(gmax, 1e-30)
+        print(f"{name:28s} loss32={loss32.item():.6f} |coords32-64|={err_c:.2e} grad relerr32-64={err_g:.2e} "
+              f"{os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,258 @@
+"""GPU (B200): the CUDA path, called through the C-ABI, against
+  (1) the committed goldens produced by the reference itself (fp32 and fp64 columns),
+  (2) the fp64 oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full size (B=32, J=18, 64^3).
+
+Parity rule (BASELINE.md 5 / SURVEY.md 8c), fp32 heatmaps:
+  coords   |a-b| / max(|b|, 1)           <= 1e-4 vs the fp32 reference
+  grads    max|a-b| / max|b| per tensor  <= 1e-4 vs the fp32 reference
+  peaked inputs (blobs): err(ours, fp64) <= max(1e-4, err(ref32, fp64))  -- the eager reference itself
+  is >1e-4 from the truth there.
+bf16 heatmaps: oracle = fp64 path on h_bf16.float(); coords <= 1e-4 rel; grad_heat is emitted in bf16:
+  |a-b| <= 2^-8 |b| + 1e-4 max|b|.
+"""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import inputs, truth
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [0, 11, 12, 13, 2, 21]
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _reset_variant():
+    import ihpr_b200
+    yield
+    ihpr_b200.set_variant(0)
+
+
+def run_ours(g_heat, gt, vis, hd, dev, dtype=torch.float32):
+    import ihpr_b200
+    h = torch.from_numpy(g_heat).to(dev).to(dtype).requires_grad_(True)
+    tg, tv, th = (torch.from_numpy(a).to(dev) for a in (gt, vis, hd))
+    loss, coords = ihpr_b200.integral_l1_loss(h, tg, tv, th, return_coords=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), coords.cpu().numpy().astype(np.float64), h.grad.float().cpu().numpy().astype(np.float64)
+
+
+def coord_err(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1.0)).max())
+
+
+def grad_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp32(name, variant, dev):
+    import ihpr_b200
+    g = load_golden(name)
+    ihpr_b200.set_variant(variant)
+    loss, coords, grad = run_ours(g["heat"], g["gt"], g["vis"], g["have_depth"], dev)
+    peaked = g["dist"] == "blobs"
+    ref32_c, ref64_c = g["ref32_coords"].astype(np.float64), g["ref64_coords"]
+    if "ref32_grad" in g:
+        ours_g, ref32_g, ref64_g = grad.reshape(-1), g["ref32_grad"].reshape(-1).astype(np.float64), g["ref64_grad"].reshape(-1)
+    else:
+        s = int(g["grad_stride"])
+        ours_g, ref32_g, ref64_g = grad.reshape(-1)[::s], g["ref32_grad_sub"].astype(np.float64), g["ref64_grad_sub"]
+    # always: within 1e-4 (or the reference's own error, if larger) of the fp64 truth
+    floor_c = max(TOL, coord_err(ref32_c, ref64_c))
+    floor_g = max(TOL, grad_err(ref32_g, ref64_g))
+    assert coord_err(coords, ref64_c) <= floor_c
+    assert grad_err(ours_g, ref64_g) <= floor_g
+    assert abs(loss - g["ref64_loss"]) <= floor_c * max(1.0, abs(g["ref64_loss"]))
+    if not peaked:
+        assert coord_err(coords, ref32_c) <= TOL
+        assert grad_err(ours_g, ref32_g) <= TOL
+        assert abs(loss - float(g["ref32_loss"])) <= TOL * max(1.0, abs(float(g["ref32_loss"])))
+    # sum_i dh_i = 0 per joint-volume
+    rows = grad.reshape(g["B"] * g["J"], -1)
+    assert np.abs(rows.sum(1)).max() <= 1e-5 * max(np.abs(rows).sum(1).max(), 1e-30)
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("name", ["randn1_b2j3_d8h8w8", "blobs_b1j4_d16h16w16", "d32_b2j17_d32h64w64", "mask_b3j5_d8h8w8"])
+def test_golden_bf16(name, variant, dev):
+    import ihpr_b200
+    g = load_golden(name)
+    ihpr_b200.set_variant(variant)
+    hb = torch.from_numpy(g["heat"]).to(torch.bfloat16)
+    heat_q = hb.float().numpy()                                    # the quantised input the oracle sees
+    loss, coords, grad = run_ours(heat_q, g["gt"], g["vis"], g["have_depth"], dev, dtype=torch.bfloat16)
+    l64, c64, g64 = truth.fwd_bwd_f64(heat_q, g["gt"], g["vis"], g["have_depth"])
+    assert coord_err(coords, c64) <= TOL
+    assert abs(loss - l64) <= TOL * max(1.0, abs(l64))
+    assert (np.abs(grad - g64) <= 2.0 ** -8 * np.abs(g64) + 1e-4 * np.abs(g64).max()).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1, 4), (1, 2, 3, 5, 4), (2, 3, 7, 3, 20), (1, 17, 32, 64, 64), (3, 18, 16, 32, 32),
+                                   (1, 2, 5, 7, 9), (2, 1, 1, 1, 1), (1, 3, 2, 3, 6), (1, 1, 128, 64, 64), (5, 2, 9, 11, 44)])
+@pytest.mark.parametrize("dist", ["randn3", "blobs"])
+def test_oracle_seeded_shapes(shape, dist, dev):
+    """ragged / tiny / odd shapes: vector path, scalar fallback (W % 4 != 0), partial chunks, nch > 1"""
+    B, J, D, H, W = shape
+    heat = inputs.make_heat(dist, B, J, D, H, W, seed=B * 1000 + W)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, seed=W, vis_mode="rand", hd_mode="alt")
+    loss, coords, grad = run_ours(heat, gt, vis, hd, dev)
+    l64, c64, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd)
+    assert coord_err(coords, c64) <= TOL
+    assert abs(loss - l64) <= TOL * max(1.0, abs(l64))
+    assert grad_err(grad, g64) <= TOL
+
+
+def test_soft_argmax_only_and_custom_grad(dev):
+    """soft_argmax(heat, J) with an arbitrary upstream gradient (not the L1 loss)"""
+    import ihpr_b200
+    B, J, D, H, W = 2, 4, 8, 16, 16
+    heat = inputs.make_heat("randn3", B, J, D, H, W, 77)
+    h = torch.from_numpy(heat).to(dev).requires_grad_(True)
+    c = ihpr_b200.soft_argmax(h, J)
+    rs = np.random.RandomState(5)
+    gc = rs.standard_normal((B, J, 3))
+    (c * torch.from_numpy(gc).to(dev).float()).sum().backward()
+    c64, m, l = truth.soft_argmax_f64(heat, J)
+    g64 = truth.soft_argmax_bwd_f64(heat, J, c64, m, l, gc.astype(np.float32).astype(np.float64))
+    assert coord_err(c.detach().cpu().numpy(), c64) <= TOL
+    assert grad_err(h.grad.cpu().numpy(), g64) <= TOL
+    with torch.no_grad():                                          # main/test.py:53 path
+        c2 = ihpr_b200.soft_argmax(h, J)
+    assert torch.equal(c2, c.detach())
+
+
+def test_grad_out_scaling_and_dropin_module(dev):
+    import ihpr_b200
+    B, J, D, H, W = 2, 3, 8, 8, 8
+    heat = inputs.make_heat("randn1", B, J, D, H, W, 9)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, 9)
+    h = torch.from_numpy(heat).to(dev).requires_grad_(True)
+    crit = ihpr_b200.install_dropin().JointLocationLoss()
+    (crit(h, *(torch.from_numpy(a).to(dev) for a in (gt, vis, hd))) * 2.5).backward()
+    _, _, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd, grad_out=2.5)
+    assert grad_err(h.grad.cpu().numpy(), g64) <= TOL
+
+
+def test_non_contiguous_and_misaligned_inputs(dev):
+    import ihpr_b200
+    B, J, D, H, W = 2, 2, 4, 8, 8
+    heat = inputs.make_heat("randn3", B, J, D, H, W, 21)
+    c64 = truth.soft_argmax_f64(heat, J)[0]
+    big = torch.zeros(B, J * D, H, 2 * W, device=dev)
+    big[..., ::2] = torch.from_numpy(heat).to(dev)
+    assert coord_err(ihpr_b200.soft_argmax(big[..., ::2], J).cpu().numpy(), c64) <= TOL
+    flat = torch.zeros(heat.size + 1, device=dev)
+    flat[1:] = torch.from_numpy(heat).to(dev).reshape(-1)
+    mis = flat[1:].view(B, J * D, H, W)                            # 4-byte aligned only -> scalar kernels
+    assert mis.data_ptr() % 16 != 0
+    assert coord_err(ihpr_b200.soft_argmax(mis, J).cpu().numpy(), c64) <= TOL
+
+
+def test_nan_inf_policy_matches_torch_softmax(dev):
+    import ihpr_b200
+    J, D, H, W = 4, 4, 8, 8
+    heat = inputs.make_heat("randn1", 1, J, D, H, W, 1).reshape(1, J, D, H, W)
+    heat[0, 0] = -np.inf                      # all -inf row -> NaN (0/0), like softmax
+    heat[0, 1, 1, 2, 3] = np.inf              # +inf -> NaN
+    heat[0, 2, 0, 0, 0] = -np.inf             # a single -inf is just a zero weight
+    heat[0, 3, 2, 2, 2] = np.nan
+    h = torch.from_numpy(heat.reshape(1, J * D, H, W)).to(dev)
+    c = ihpr_b200.soft_argmax(h, J).cpu().numpy()[0]
+    assert np.isnan(c[0]).all() and np.isnan(c[1]).all() and np.isnan(c[3]).all()
+    ref = truth.soft_argmax_f64(heat.reshape(1, J * D, H, W), J)[0][0]
+    assert np.isfinite(c[2]).all() and np.abs(c[2] - ref[2]).max() <= 1e-3
+
+
+def test_full_size_properties_and_determinism(dev):
+    """BASELINE.json full size: B=32, J=18, 64^3 fp32 (576 MiB) -- properties that need no CPU oracle pass,
+    plus an oracle check on a slice of joint-volumes."""
+    import ihpr_b200
+    B, J, D, H, W = 32, 18, 64, 64, 64
+    gen = torch.Generator(device=dev).manual_seed(0)
+    h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
+    gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 0, "rand", "alt"))
+    loss, coords = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True)
+    loss.backward()
+    g1, c1, l1 = h.grad.clone(), coords.clone(), loss.detach().clone()
+    # bit-reproducible across runs (fixed merge order, no float atomics)
+    h.grad = None
+    loss2, coords2 = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True)
+    loss2.backward()
+    assert torch.equal(coords2, c1) and torch.equal(loss2.detach(), l1) and torch.equal(h.grad, g1)
+    # loss recomputed from coords with plain torch (loss.py:49-52)
+    t = (coords - gt).abs() * vis.view(B, J, 1)
+    want = ((t[..., 0] + t[..., 1] + t[..., 2] * hd.view(B, 1)) / 3).mean()
+    assert abs(loss.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+    # gradient rows sum to zero; masked joints have exactly zero gradient
+    rows = g1.view(B * J, -1)
+    assert (rows.sum(1).abs() <= 1e-4 * rows.abs().sum(1).clamp_min(1e-30)).all()
+    dead = (vis.view(-1) == 0)
+    assert dead.any() and rows[dead].abs().max().item() == 0.0
+    # shift invariance: h + c gives the same coords
+    with torch.no_grad():
+        c_shift = ihpr_b200.soft_argmax(h.detach() + 3.0, J)
+    assert (c_shift - c1).abs().max().item() <= 2e-3
+    # oracle on the first and last sample
+    for b in (0, B - 1):
+        hb = h.detach()[b:b + 1].cpu().numpy()
+        c64, m, l = truth.soft_argmax_f64(hb, J)
+        assert coord_err(c1[b:b + 1].cpu().numpy(), c64) <= TOL
+    # all variants agree to rounding on the full size
+    for v in (11, 2):
+        ihpr_b200.set_variant(v)
+        with torch.no_grad():
+            cv = ihpr_b200.soft_argmax(h.detach(), J)
+        assert (cv - c1).abs().max().item() <= 1e-3
+
+
+def test_streams_and_threads(dev):
+    """the reference calls its criterion from one Python thread per GPU (balanced_parallel.py:149-173);
+    here: several threads, each on its own stream of cuda:0, concurrently."""
+    import ihpr_b200
+    B, J, D, H, W = 2, 18, 16, 32, 32
+    heat = inputs.make_heat("randn3", B, J, D, H, W, 31)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, 31)
+    l64, c64, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd)
+    errs = []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream(dev)
+            with torch.cuda.stream(s):
+                for _ in range(5):
+                    loss, coords, grad = run_ours(heat, gt, vis, hd, dev)
+                    assert coord_err(coords, c64) <= TOL and grad_err(grad, g64) <= TOL
+        except Exception as e:      # noqa
+            errs.append(e)
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+
+def test_host_buffer_entry_point(dev):
+    import ihpr_b200
+    B, J, D, H, W = 5, 3, 8, 16, 16
+    heat = inputs.make_heat("randn3", B, J, D, H, W, 41)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, 41, "rand", "alt")
+    th = torch.from_numpy(heat).pin_memory()
+    loss, coords, grad = ihpr_b200.integral_l1_fwd_bwd_host(th, torch.from_numpy(gt), torch.from_numpy(vis), torch.from_numpy(hd),
+                                                            grad_out=1.0, slices=3)
+    l64, c64, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd)
+    assert abs(loss.item() - l64) <= TOL * max(1.0, abs(l64))
+    assert coord_err(coords.numpy(), c64) <= TOL and grad_err(grad.numpy(), g64) <= TOL
+    assert ihpr_b200.last_launch_count() == 2 * 3 + 1

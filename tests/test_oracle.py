@@ -1,0 +1,132 @@
+"""CPU: the oracle restatements against the goldens generated from the reference itself, plus the
+analytic known-answer tests of SURVEY.md 8c.  Tolerances are written next to each check."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import inputs, truth
+from oracle.soft_argmax_ref import RefJointLocationLoss, ref_fwd_bwd, ref_soft_argmax
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_truth64_matches_reference_fp64(name):
+    g = load_golden(name)
+    loss, coords, grad = truth.fwd_bwd_f64(g["heat"], g["gt"], g["vis"], g["have_depth"])
+    assert abs(loss - g["ref64_loss"]) <= 1e-9 * max(1.0, abs(g["ref64_loss"]))
+    assert np.abs(coords - g["ref64_coords"]).max() <= 1e-9 * max(g["D"], g["H"], g["W"])
+    if "ref64_grad" in g:
+        ref = g["ref64_grad"]
+        assert np.abs(grad - ref).max() <= 1e-9 * np.abs(ref).max()
+    else:
+        sub = grad.reshape(-1)[::int(g["grad_stride"])]
+        assert np.abs(sub - g["ref64_grad_sub"]).max() <= 1e-9 * g["ref64_grad_max"]
+        assert abs(np.abs(grad).sum() - g["ref64_grad_abssum"]) <= 1e-9 * g["ref64_grad_abssum"]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_torch_restatement_matches_reference_fp32(name):
+    # same ATen op sequence as the reference; bit-identical where the goldens were made, so only
+    # summation-order noise (other CPU, other thread count) is allowed: 2e-6 relative.
+    g = load_golden(name)
+    th, tgt, tvis, thd = (torch.from_numpy(g[k]) for k in ("heat", "gt", "vis", "have_depth"))
+    loss, coords, grad = ref_fwd_bwd(th, tgt, tvis, thd)
+    assert abs(loss.item() - g["ref32_loss"]) <= 2e-6 * max(1.0, abs(g["ref32_loss"]))
+    assert np.abs(coords.numpy() - g["ref32_coords"]).max() <= 2e-6 * max(g["D"], g["H"], g["W"]) * 4
+    gn = grad.numpy().reshape(-1)
+    ref = g["ref32_grad"].reshape(-1) if "ref32_grad" in g else None
+    if ref is None:
+        gn = gn[::int(g["grad_stride"])]
+        ref = g["ref32_grad_sub"]
+    assert np.abs(gn - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-30)
+
+
+def _coords64(heat, J):
+    return truth.soft_argmax_f64(heat, J)[0]
+
+
+def test_kat_uniform_heatmap_gives_centre():
+    B, J, D, H, W = 1, 3, 6, 10, 8
+    c = _coords64(np.zeros((B, J * D, H, W), np.float32), J)
+    assert np.allclose(c[..., 0], (W - 1) / 2, atol=1e-12)
+    assert np.allclose(c[..., 1], (H - 1) / 2, atol=1e-12)
+    assert np.allclose(c[..., 2], (D - 1) / 2, atol=1e-12)
+    ct = ref_soft_argmax(torch.zeros(B, J * D, H, W), J).numpy()
+    assert np.allclose(ct, c, atol=1e-4)
+
+
+def test_kat_one_hot_peak_and_axis_order():
+    B, J, D, H, W = 1, 2, 5, 7, 12      # D != H != W: catches axis mix-ups; order is x(W), y(H), z(D)
+    h = np.zeros((B, J, D, H, W), np.float32)
+    h[0, 0, 3, 5, 9] = 200.0
+    h[0, 1, 1, 6, 2] = 200.0
+    c = _coords64(h.reshape(B, J * D, H, W), J)
+    assert np.allclose(c[0, 0], [9, 5, 3], atol=1e-9) and np.allclose(c[0, 1], [2, 6, 1], atol=1e-9)
+    ct = ref_soft_argmax(torch.from_numpy(h.reshape(B, J * D, H, W)), J).numpy()
+    assert np.allclose(ct, c, atol=1e-4)
+
+
+def test_kat_shift_invariance_and_large_magnitude():
+    h = inputs.make_heat("randn3", 1, 2, 8, 8, 8, 0)
+    c0 = _coords64(h, 2)
+    assert np.abs(_coords64(h + np.float32(512.0), 2) - c0).max() <= 1e-3     # fp32 input rounding only
+    big = inputs.make_heat("large", 1, 2, 8, 8, 8, 0)
+    assert np.isfinite(_coords64(big, 2)).all()
+    assert np.isfinite(ref_soft_argmax(torch.from_numpy(big), 2).numpy()).all()
+
+
+def test_kat_separable_heatmap():
+    D, H, W = 6, 9, 8
+    rs = np.random.RandomState(0)
+    a, b, c = rs.randn(W), rs.randn(H), rs.randn(D)
+    h = (c[:, None, None] + b[None, :, None] + a[None, None, :]).astype(np.float32).reshape(1, D, H, W)
+    got = _coords64(h, 1)[0, 0]
+
+    def sa(v):
+        p = np.exp(v - v.max()); p /= p.sum()
+        return (p * np.arange(len(v))).sum()
+    assert np.allclose(got, [sa(a), sa(b), sa(c)], atol=1e-5)
+
+
+def test_kat_w_flip():
+    # main/test.py:73: x' = W - x - 1 for a W-flipped heatmap
+    J, D, H, W = 2, 4, 6, 8
+    h = inputs.make_heat("randn3", 1, J, D, H, W, 3)
+    c = _coords64(h, J)
+    cf = _coords64(np.ascontiguousarray(h[..., ::-1]), J)
+    assert np.allclose(cf[..., 0], W - 1 - c[..., 0], atol=1e-9)
+    assert np.allclose(cf[..., 1:], c[..., 1:], atol=1e-9)
+
+
+def test_kat_gradient_sums_to_zero_and_masks():
+    B, J, D, H, W = 2, 3, 4, 6, 8
+    h = inputs.make_heat("randn3", B, J, D, H, W, 4)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, 4)
+    _, _, g = truth.fwd_bwd_f64(h, gt, vis, hd)
+    assert np.abs(g.reshape(B * J, -1).sum(1)).max() <= 1e-12
+    loss0, _, g0 = truth.fwd_bwd_f64(h, gt, np.zeros_like(vis), hd)
+    assert loss0 == 0.0 and np.abs(g0).max() == 0.0
+    # have_depth = 0 removes the z term: the loss no longer depends on gt z
+    gt2 = gt.copy(); gt2[..., 2] += 5
+    l1, _, _ = truth.fwd_bwd_f64(h, gt, vis, np.zeros_like(hd))
+    l2, _, _ = truth.fwd_bwd_f64(h, gt2, vis, np.zeros_like(hd))
+    assert l1 == l2
+    tl = RefJointLocationLoss()(torch.from_numpy(h), torch.from_numpy(gt), torch.from_numpy(vis), torch.zeros(B, 1))
+    assert abs(tl.item() - l1) <= 1e-5
+
+
+def test_fp32_c_port_close_to_truth():
+    B, J, D, H, W = 2, 3, 8, 8, 8
+    h = inputs.make_heat("randn3", B, J, D, H, W, 5)
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, 5, "rand", "alt")
+    loss, coords, g = truth.fwd_bwd_f32_port(h, gt, vis, hd)
+    l64, c64, g64 = truth.fwd_bwd_f64(h, gt, vis, hd)
+    assert abs(loss - l64) <= 1e-5 and np.abs(coords - c64).max() <= 1e-4
+    assert np.abs(g - g64).max() <= 1e-5 * np.abs(g64).max()
+
+
+def test_targets_must_not_require_grad():
+    h = torch.zeros(1, 8, 2, 2)
+    gt = torch.zeros(1, 2, 3, requires_grad=True)
+    with pytest.raises(AssertionError):
+        RefJointLocationLoss()(h, gt, torch.ones(1, 2, 1), torch.ones(1, 1))
