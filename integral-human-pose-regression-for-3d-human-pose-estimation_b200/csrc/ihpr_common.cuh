@@ -42,31 +42,43 @@ __device__ __forceinline__ float ex2(float x) {
 
 // ---------------------------------------------------------------------------------------------
 // Online-softmax partial state of one joint-volume: l = sum 2^(h*log2e - c), s* = sum of the same
-// weights times the voxel coordinate.  c = fl(m * log2e) is a pure function of the running max m,
-// so partials from different threads / CTAs re-base exactly.  m == -inf means "nothing seen yet"
-// (c = 0 keeps the arithmetic finite); +inf / NaN inputs turn the row into NaN like torch's softmax.
+// weights times the voxel coordinate.  c = fl(m * log2e) is a pure function of the reference point m,
+// so partials from different threads / CTAs re-base exactly.  The reference point is LAZY: it is only
+// raised when a batch maximum exceeds it by more than kRebaseSlack (weights then stay below e^30, far
+// from fp32 overflow even summed over 2^30 voxels), so the re-base branch runs once per joint-volume on
+// ordinary data instead of once per batch; the true maximum is tracked separately in mx and the final
+// (m, l) pair is re-based to it.  m == -inf means "nothing seen yet" (c = 0 keeps the arithmetic
+// finite); +inf / NaN inputs turn the row into NaN like torch's softmax.
+constexpr float kRebaseSlack = 30.f;
 struct Acc {
-    float m, c, l, sx, sy, sz;
+    float m, c, lim, mx, l, sx, sy, sz;
     __device__ __forceinline__ void reset() {
-        m = -INFINITY;
+        m = lim = mx = -INFINITY;
         c = 0.f;
         l = sx = sy = sz = 0.f;
     }
 };
 __device__ __forceinline__ float safe_c(float m) { return (m == -INFINITY) ? 0.f : m * kLog2e; }
 
-// raise the running max to cmax (> a.m) and re-base the sums
+// move the reference point up to cmax (> a.m) and re-base the sums
 __device__ __forceinline__ void acc_raise(Acc& a, float cmax) {
     const float cn = safe_c(cmax);
     const float s = (a.m == -INFINITY) ? 0.f : ex2(a.c - cn);
     a.l *= s; a.sx *= s; a.sy *= s; a.sz *= s;
-    a.m = cmax; a.c = cn;
+    a.m = cmax; a.c = cn; a.lim = cmax + kRebaseSlack;
+}
+// bookkeeping for a batch whose maximum is cmax, before its weights are accumulated
+__device__ __forceinline__ void acc_see_max(Acc& a, float cmax) {
+    a.mx = fmaxf(a.mx, cmax);
+    if (cmax > a.lim) acc_raise(a, cmax);
 }
 
 __device__ __forceinline__ Acc acc_merge(const Acc& a, const Acc& b) {
     Acc o;
     o.m = fmaxf(a.m, b.m);
     o.c = safe_c(o.m);
+    o.mx = fmaxf(a.mx, b.mx);
+    o.lim = o.m + kRebaseSlack;
     const float fa = (a.m == -INFINITY) ? 0.f : ex2(a.c - o.c);
     const float fb = (b.m == -INFINITY) ? 0.f : ex2(b.c - o.c);
     o.l = a.l * fa + b.l * fb;
@@ -81,6 +93,7 @@ __device__ __forceinline__ Acc acc_warp_merge(Acc a) {
     for (int o = 16; o > 0; o >>= 1) {
         Acc b;
         b.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+        b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
         b.l = __shfl_xor_sync(0xffffffffu, a.l, o);
         b.sx = __shfl_xor_sync(0xffffffffu, a.sx, o);
         b.sy = __shfl_xor_sync(0xffffffffu, a.sy, o);
@@ -88,6 +101,26 @@ __device__ __forceinline__ Acc acc_warp_merge(Acc a) {
         b.c = safe_c(b.m);
         a = acc_merge(a, b);
     }
+    return a;
+}
+
+// partial <-> 8-float slot {m, l, sx, sy, sz, mx, -, -}
+__device__ __forceinline__ void partial_to_smem(volatile float* d, const Acc& a) {
+    d[0] = a.m; d[1] = a.l; d[2] = a.sx; d[3] = a.sy; d[4] = a.sz; d[5] = a.mx;
+}
+__device__ __forceinline__ Acc partial_from_smem(const volatile float* s) {
+    Acc a;
+    a.m = s[0]; a.l = s[1]; a.sx = s[2]; a.sy = s[3]; a.sz = s[4]; a.mx = s[5];
+    a.c = safe_c(a.m); a.lim = a.m + kRebaseSlack;
+    return a;
+}
+__device__ __forceinline__ void partial_to_global(float* d, const Acc& a) {
+    __stcg(d + 0, a.m); __stcg(d + 1, a.l); __stcg(d + 2, a.sx); __stcg(d + 3, a.sy); __stcg(d + 4, a.sz); __stcg(d + 5, a.mx);
+}
+__device__ __forceinline__ Acc partial_from_global(const float* s) {
+    Acc a;
+    a.m = __ldcg(s + 0); a.l = __ldcg(s + 1); a.sx = __ldcg(s + 2); a.sy = __ldcg(s + 3); a.sz = __ldcg(s + 4); a.mx = __ldcg(s + 5);
+    a.c = safe_c(a.m); a.lim = a.m + kRebaseSlack;
     return a;
 }
 
@@ -206,6 +239,7 @@ struct Geometry {
     uint32_t nch;       // chunks per joint-volume = ceil(N / CE)
     uint64_t Gt;        // total chunks = R * nch
     FastDiv divF;       // quads per x-row (W/4)         [vector paths]
+    FastDiv divFv;      // 16-byte vectors per x-row (W/4 fp32, W/8 bf16); d = 0 when W is not a multiple
     FastDiv divW;       // W                             [scalar path]
     FastDiv divH;       // H
 };

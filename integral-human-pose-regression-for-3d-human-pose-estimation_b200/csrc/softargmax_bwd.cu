@@ -9,81 +9,9 @@
 //     g_c = grad_out * sign(coord_c - gt_c) * vis * w_c / (3*B*J)      (loss.py:49-52)
 // is formed per joint-volume in the kernel prologue instead of by ~10 tiny launches.
 // Same persistent equal-bytes split as the forward; no cross-CTA communication at all.
-#include "ihpr_common.cuh"
+#include "ihpr_device.cuh"
 
 namespace ihpr {
-
-struct RowK {
-    float c;            // safe m*log2e
-    float gx, gy, gz;   // upstream gradient, pre-divided by l
-    float cx, cy, cz;   // expected coordinate
-};
-
-__device__ __forceinline__ float sgn(float d) { return (float)((d > 0.f) - (d < 0.f)); }
-
-__device__ __forceinline__ RowK load_row(const BwdParams& p, uint32_t r) {
-    RowK k;
-    const float m = __ldg(p.stats + 2 * (size_t)r), l = __ldg(p.stats + 2 * (size_t)r + 1);
-    k.c = safe_c(m);
-    k.cx = __ldg(p.coords + 3 * (size_t)r);
-    k.cy = __ldg(p.coords + 3 * (size_t)r + 1);
-    k.cz = __ldg(p.coords + 3 * (size_t)r + 2);
-    float gx, gy, gz;
-    if (p.grad_coords) {
-        gx = __ldg(p.grad_coords + 3 * (size_t)r);
-        gy = __ldg(p.grad_coords + 3 * (size_t)r + 1);
-        gz = __ldg(p.grad_coords + 3 * (size_t)r + 2);
-    } else {
-        const float s = __ldg(p.grad_out) * __ldg(p.vis + r) * p.loss_scale;
-        gx = s * sgn(k.cx - __ldg(p.gt + 3 * (size_t)r));
-        gy = s * sgn(k.cy - __ldg(p.gt + 3 * (size_t)r + 1));
-        gz = s * sgn(k.cz - __ldg(p.gt + 3 * (size_t)r + 2)) * __ldg(p.have_depth + r / p.g.J);
-    }
-    const float il = 1.0f / l;
-    k.gx = gx * il; k.gy = gy * il; k.gz = gz * il;
-    return k;
-}
-
-__device__ __forceinline__ void bwd_quad(const RowK& k, const float (&v)[4], float (&o)[4], float xf, float yf, float zf) {
-    const float base = fmaf(k.gz, zf - k.cz, fmaf(k.gy, yf - k.cy, k.gx * (xf - k.cx)));
-    o[0] = ex2(fmaf(v[0], kLog2e, -k.c)) * base;
-    o[1] = ex2(fmaf(v[1], kLog2e, -k.c)) * (base + k.gx);
-    o[2] = ex2(fmaf(v[2], kLog2e, -k.c)) * fmaf(2.f, k.gx, base);
-    o[3] = ex2(fmaf(v[3], kLog2e, -k.c)) * fmaf(3.f, k.gx, base);
-}
-
-template <typename T, int U, int NC, typename Loader>
-__device__ __forceinline__ void bwd_chunk(const RowK& k, const Geometry& g, uint32_t n_vec, uint32_t qbase, int tid, uint8_t* dst,
-                                          Loader load) {
-    constexpr int QPV = Elem<T>::QPV;
-    const uint32_t F = g.divF.d;
-    for (uint32_t base = 0; base < n_vec; base += NC * U) {
-        uint4 raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t iv = base + u * NC + tid;
-            if (iv < n_vec) raw[u] = load(iv);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t iv = base + u * NC + tid;
-            if (iv < n_vec) {
-                float v[QPV][4], o[QPV][4];
-                Elem<T>::unpack(raw[u], v);
-#pragma unroll
-                for (int q = 0; q < QPV; ++q) {
-                    const uint32_t qi = qbase + iv * QPV + q;
-                    const uint32_t zy = fdiv(qi, g.divF);
-                    const uint32_t x4 = qi - zy * F;
-                    const uint32_t z = fdiv(zy, g.divH);
-                    const uint32_t y = zy - z * g.divH.d;
-                    bwd_quad(k, v[q], o[q], u2f(x4 << 2), u2f(y), u2f(z));
-                }
-                st_stream16(dst + (size_t)iv * 16, Elem<T>::pack(o));
-            }
-        }
-    }
-}
 
 template <typename T, int CHUNK_BYTES, int STAGES, int NCW, int MINB>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB) bwd_ring_kernel(const BwdParams p) {
@@ -130,7 +58,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) bwd_ring_kernel(const Bwd
     constexpr int QPV = Elem<T>::QPV;
     const int tid = threadIdx.x - 32;
     uint8_t* out = reinterpret_cast<uint8_t*>(p.grad_heat);
+    const bool fast = fast_ok<NC, VPC>(g);
+    const uint32_t Fv = fast ? g.divFv.d : 1;
+    const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NC / Fv), hf = u2f((uint32_t)g.H);
     RowK rk = load_row(p, r);
+    float tx[4 * QPV];
+    make_tx<4 * QPV>(rk, x0f, tx);
     uint32_t it = 0;
     for (uint64_t gi = g_lo; gi < g_hi; ++gi, ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -138,13 +71,19 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) bwd_ring_kernel(const Bwd
         const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
         mbar_wait(full + s, ph);
         const uint8_t* st = ring + (size_t)s * CHUNK_BYTES;
-        bwd_chunk<T, U, NC>(rk, g, n_vec, e0 >> 2, tid, out + ((size_t)r * g.N + e0) * sizeof(T),
-                            [&](uint32_t iv) { return lds16(st + (size_t)iv * 16); });
+        uint8_t* dst = out + ((size_t)r * g.N + e0) * sizeof(T);
+        auto load = [&](uint32_t iv) { return lds16(st + (size_t)iv * 16); };
+        if (fast) {
+            if (n_vec == VPC) bwd_chunk_fast<T, U, NC, VPC, true>(rk, tx, g, n_vec, k * VPC, tid, rsf, hf, dst, load);
+            else bwd_chunk_fast<T, U, NC, VPC, false>(rk, tx, g, n_vec, k * VPC, tid, rsf, hf, dst, load);
+        } else {
+            bwd_chunk<T, U, NC>(rk, g, n_vec, e0 >> 2, tid, dst, load);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
         if (++k == g.nch) {
             k = 0; ++r;
-            if (gi + 1 < g_hi) rk = load_row(p, r);
+            if (gi + 1 < g_hi) { rk = load_row(p, r); make_tx<4 * QPV>(rk, x0f, tx); }
         }
     }
 }
@@ -159,16 +98,29 @@ __global__ void __launch_bounds__(NT, MINB) bwd_direct_kernel(const BwdParams p)
     uint32_t k = (uint32_t)(g_lo - (uint64_t)r * g.nch);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.heat);
     uint8_t* out = reinterpret_cast<uint8_t*>(p.grad_heat);
+    constexpr int VPC = NT * U;
+    const int tid = threadIdx.x;
+    const bool fast = fast_ok<NT, VPC>(g);
+    const uint32_t Fv = fast ? g.divFv.d : 1;
+    const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NT / Fv), hf = u2f((uint32_t)g.H);
     RowK rk = load_row(p, r);
+    float tx[4 * QPV];
+    make_tx<4 * QPV>(rk, x0f, tx);
     for (uint64_t gi = g_lo; gi < g_hi; ++gi) {
         const uint32_t e0 = k * g.CE;
         const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
         const size_t off = ((size_t)r * g.N + e0) * sizeof(T);
         const uint8_t* cp = src + off;
-        bwd_chunk<T, U, NT>(rk, g, n_vec, e0 >> 2, threadIdx.x, out + off, [&](uint32_t iv) { return ld_stream16(cp + (size_t)iv * 16); });
+        auto load = [&](uint32_t iv) { return ld_stream16(cp + (size_t)iv * 16); };
+        if (fast) {
+            if (n_vec == VPC) bwd_chunk_fast<T, U, NT, VPC, true>(rk, tx, g, n_vec, k * VPC, tid, rsf, hf, out + off, load);
+            else bwd_chunk_fast<T, U, NT, VPC, false>(rk, tx, g, n_vec, k * VPC, tid, rsf, hf, out + off, load);
+        } else {
+            bwd_chunk<T, U, NT>(rk, g, n_vec, e0 >> 2, tid, out + off, load);
+        }
         if (++k == g.nch) {
             k = 0; ++r;
-            if (gi + 1 < g_hi) rk = load_row(p, r);
+            if (gi + 1 < g_hi) { rk = load_row(p, r); make_tx<4 * QPV>(rk, x0f, tx); }
         }
     }
 }
@@ -238,7 +190,9 @@ static void launch_bwd_t(const BwdParams& p, bool vec_ok, int variant, int num_s
         case 11: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
         case 12: return launch_ring<T, 16384, 12, 16, 1>(p, num_sms, s);
         case 13: return launch_ring<T, 16384, 6, 8, 2>(p, num_sms, s);
-        default: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
+        case 14: return launch_ring<T, 32768, 3, 16, 2>(p, num_sms, s);
+        case 1: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
+        default: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
     }
 }
 

@@ -15,136 +15,9 @@
 //                   mbarrier full/empty pairs), NCW consumer warps read the ring with 128-bit LDS.
 //   direct kernel : every thread issues U 128-bit streaming global loads per step (also the scalar
 //                   fallback for shapes with W % 4 != 0 or unaligned bases).
-#include "ihpr_common.cuh"
+#include "ihpr_device.cuh"
 
 namespace ihpr {
-
-// ---------------------------------------------------------------------------------------------
-// row finalisation shared by all forward kernels.  Called by all `nthreads` consumer threads.
-template <int NW>
-__device__ __forceinline__ void flush_row(const FwdParams& p, int r, Acc a, float (*red)[8], int bar_id, int wid, int lane,
-                                          uint32_t cta, uint32_t G) {
-    a = acc_warp_merge(a);
-    if (lane == 0) {
-        red[wid][0] = a.m; red[wid][1] = a.l; red[wid][2] = a.sx; red[wid][3] = a.sy; red[wid][4] = a.sz;
-    }
-    named_bar_sync(bar_id, NW * 32);
-    if (wid == 0) {
-        Acc b;
-        b.reset();
-        if (lane < NW) {
-            b.m = red[lane][0]; b.l = red[lane][1]; b.sx = red[lane][2]; b.sy = red[lane][3]; b.sz = red[lane][4];
-            b.c = safe_c(b.m);
-        }
-        b = acc_warp_merge(b);
-
-        const Geometry& g = p.g;
-        const uint64_t g0 = (uint64_t)r * g.nch;
-        const uint32_t c_first = owner_of(g0, g.Gt, G);
-        const uint32_t c_last = owner_of(g0 + g.nch - 1, g.Gt, G);
-        const int ncontrib = (int)(c_last - c_first) + 1;
-        bool last = true;
-        if (ncontrib > 1) {
-            float* slot = p.partials + ((size_t)r * p.maxslots + (cta - c_first)) * 8;
-            int ticket = 0;
-            if (lane == 0) {
-                __stcg(slot + 0, b.m); __stcg(slot + 1, b.l); __stcg(slot + 2, b.sx);
-                __stcg(slot + 3, b.sy); __stcg(slot + 4, b.sz);
-                __threadfence();
-                ticket = atomicAdd(p.row_count + r, 1);
-            }
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            last = (ticket == ncontrib - 1);
-            if (last) {
-                __threadfence();
-                b.reset();
-                const float* base = p.partials + (size_t)r * p.maxslots * 8;
-                for (int s = lane; s < ncontrib; s += 32) {
-                    Acc t;
-                    t.m = __ldcg(base + s * 8 + 0); t.l = __ldcg(base + s * 8 + 1); t.sx = __ldcg(base + s * 8 + 2);
-                    t.sy = __ldcg(base + s * 8 + 3); t.sz = __ldcg(base + s * 8 + 4);
-                    t.c = safe_c(t.m);
-                    b = acc_merge(b, t);
-                }
-                b = acc_warp_merge(b);
-                if (lane == 0) p.row_count[r] = 0;      // leave the workspace zeroed for the next launch
-            }
-        }
-        if (last) {
-            const float inv = 1.0f / b.l;
-            const float cx = b.sx * inv, cy = b.sy * inv, cz = b.sz * inv;
-            int t2 = 0;
-            if (lane == 0) {
-                p.coords[3 * (size_t)r + 0] = cx;
-                p.coords[3 * (size_t)r + 1] = cy;
-                p.coords[3 * (size_t)r + 2] = cz;
-                if (p.stats) { p.stats[2 * (size_t)r] = b.m; p.stats[2 * (size_t)r + 1] = b.l; }
-                if (p.gt) {
-                    // loss.py:49-50: (|dx| + |dy| + |dz| * have_depth) * vis / 3
-                    const float v = p.vis[r], hd = p.have_depth[r / g.J];
-                    const float lx = fabsf(cx - p.gt[3 * (size_t)r]) * v;
-                    const float ly = fabsf(cy - p.gt[3 * (size_t)r + 1]) * v;
-                    const float lz = fabsf(cz - p.gt[3 * (size_t)r + 2]) * v;
-                    __stcg(p.row_loss + r, (lx + ly + lz * hd) / 3.f);
-                    __threadfence();
-                    t2 = atomicAdd(p.done_rows, 1);
-                }
-            }
-            if (p.gt) {
-                t2 = __shfl_sync(0xffffffffu, t2, 0);
-                if (t2 == g.R - 1) {            // every joint-volume is final: loss.py:52 mean()
-                    __threadfence();
-                    float s = 0.f;
-                    for (int i = lane; i < g.R; i += 32) s += __ldcg(p.row_loss + i);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) { p.loss[0] = s / (float)g.R; *p.done_rows = 0; }
-                }
-            }
-        }
-    }
-    named_bar_sync(bar_id, NW * 32);
-}
-
-// ---------------------------------------------------------------------------------------------
-// consume `n_vec` 16-byte vectors of one chunk; LOADER(i) returns vector i of the chunk
-template <typename T, int U, int NC, typename Loader>
-__device__ __forceinline__ void consume_chunk(Acc& a, const Geometry& g, uint32_t n_vec, uint32_t qbase, int tid, Loader load) {
-    constexpr int QPV = Elem<T>::QPV;
-    const uint32_t F = g.divF.d;
-    for (uint32_t base = 0; base < n_vec; base += NC * U) {
-        float v[U][QPV][4];
-        uint4 raw[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t iv = base + u * NC + tid;
-            raw[u] = (iv < n_vec) ? load(iv) : (sizeof(T) == 4 ? make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u)
-                                                               : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u));
-        }
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            Elem<T>::unpack(raw[u], v[u]);
-#pragma unroll
-            for (int q = 0; q < QPV; ++q)
-                cmax = fmaxf(cmax, fmaxf(fmaxf(v[u][q][0], v[u][q][1]), fmaxf(v[u][q][2], v[u][q][3])));
-        }
-        if (cmax > a.m) acc_raise(a, cmax);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t iv = base + u * NC + tid;
-#pragma unroll
-            for (int q = 0; q < QPV; ++q) {
-                const uint32_t qi = qbase + iv * QPV + q;
-                const uint32_t zy = fdiv(qi, g.divF);
-                const uint32_t x4 = qi - zy * F;
-                const uint32_t z = fdiv(zy, g.divH);
-                const uint32_t y = zy - z * g.divH.d;
-                acc_quad(a, v[u][q], u2f(x4 << 2), u2f(y), u2f(z));
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // ring kernel
@@ -154,7 +27,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) fwd_ring_kernel(const Fwd
     uint8_t* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * CHUNK_BYTES);
     uint64_t* empty = full + STAGES;
-    float(*red)[8] = reinterpret_cast<float(*)[8]>(empty + STAGES);
+    constexpr int NBUF = STAGES + 1;
+    float(*pbuf)[8] = reinterpret_cast<float(*)[8]>(empty + STAGES);        // [NBUF][NCW][8]
+    int* pcnt = reinterpret_cast<int*>(pbuf + NBUF * NCW);                  // [NBUF]
 
     const Geometry& g = p.g;
     const uint32_t G = gridDim.x, cta = blockIdx.x;
@@ -163,6 +38,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) fwd_ring_kernel(const Fwd
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+        for (int b = 0; b < NBUF; ++b) pcnt[b] = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -195,25 +71,38 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) fwd_ring_kernel(const Fwd
     constexpr int U = (VPC / NC) < 1 ? 1 : ((VPC / NC) > 4 ? 4 : (VPC / NC));
     constexpr int QPV = Elem<T>::QPV;
     const int tid = threadIdx.x - 32, wid = warp - 1;
+    const bool fast = fast_ok<NC, VPC>(g);
+    const uint32_t Fv = fast ? g.divFv.d : 1;
+    const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NC / Fv), hf = u2f((uint32_t)g.H);
     Acc a;
     a.reset();
-    uint32_t it = 0;
+    uint32_t it = 0, rowseq = 0;
     for (uint64_t gi = g_lo; gi < g_hi; ++gi, ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         const uint32_t e0 = k * g.CE;
         const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
         mbar_wait(full + s, ph);
         const uint8_t* st = ring + (size_t)s * CHUNK_BYTES;
-        consume_chunk<T, U, NC>(a, g, n_vec, e0 >> 2, tid, [&](uint32_t iv) { return lds16(st + (size_t)iv * 16); });
+        auto load = [&](uint32_t iv) { return lds16(st + (size_t)iv * 16); };
+        if (fast) {
+            if (n_vec == VPC) consume_chunk_fast<T, U, NC, VPC, true>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
+            else consume_chunk_fast<T, U, NC, VPC, false>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
+        } else {
+            consume_chunk<T, U, NC>(a, g, n_vec, e0 >> 2, tid, load);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
         if (++k == g.nch) {
-            flush_row<NCW>(p, (int)r, a, red, 1, wid, lane, cta, G);
+            if (fast) a.sx = fmaf(x0f, a.l, a.sx);
+            flush_row_async<NCW, NBUF>(p, (int)r, a, pbuf, pcnt, rowseq++, wid, lane, cta, G);
             a.reset();
             k = 0; ++r;
         }
     }
-    if (k != 0) flush_row<NCW>(p, (int)r, a, red, 1, wid, lane, cta, G);
+    if (k != 0) {
+        if (fast) a.sx = fmaf(x0f, a.l, a.sx);
+        flush_row_async<NCW, NBUF>(p, (int)r, a, pbuf, pcnt, rowseq++, wid, lane, cta, G);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -229,20 +118,34 @@ __global__ void __launch_bounds__(NT, MINB) fwd_direct_kernel(const FwdParams p)
     uint32_t r = (uint32_t)(g_lo / g.nch);
     uint32_t k = (uint32_t)(g_lo - (uint64_t)r * g.nch);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.heat);
+    constexpr int VPC = NT * U;
+    const bool fast = fast_ok<NT, VPC>(g);
+    const uint32_t Fv = fast ? g.divFv.d : 1;
+    const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NT / Fv), hf = u2f((uint32_t)g.H);
     Acc a;
     a.reset();
     for (uint64_t gi = g_lo; gi < g_hi; ++gi) {
         const uint32_t e0 = k * g.CE;
         const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
         const uint8_t* cp = src + ((size_t)r * g.N + e0) * sizeof(T);
-        consume_chunk<T, U, NT>(a, g, n_vec, e0 >> 2, tid, [&](uint32_t iv) { return ld_stream16(cp + (size_t)iv * 16); });
+        auto load = [&](uint32_t iv) { return ld_stream16(cp + (size_t)iv * 16); };
+        if (fast) {
+            if (n_vec == VPC) consume_chunk_fast<T, U, NT, VPC, true>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
+            else consume_chunk_fast<T, U, NT, VPC, false>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
+        } else {
+            consume_chunk<T, U, NT>(a, g, n_vec, e0 >> 2, tid, load);
+        }
         if (++k == g.nch) {
+            if (fast) a.sx = fmaf(x0f, a.l, a.sx);
             flush_row<NT / 32>(p, (int)r, a, red, 1, wid, lane, cta, G);
             a.reset();
             k = 0; ++r;
         }
     }
-    if (k != 0) flush_row<NT / 32>(p, (int)r, a, red, 1, wid, lane, cta, G);
+    if (k != 0) {
+        if (fast) a.sx = fmaf(x0f, a.l, a.sx);
+        flush_row<NT / 32>(p, (int)r, a, red, 1, wid, lane, cta, G);
+    }
 }
 
 // scalar fallback: any shape / alignment (W % 4 != 0, odd N, unaligned base pointer)
@@ -264,7 +167,7 @@ __global__ void __launch_bounds__(NT) fwd_scalar_kernel(const FwdParams p) {
         const T* cp = src + (size_t)r * g.N + e0;
         for (uint32_t i = threadIdx.x; i < n_el; i += NT) {
             const float h = Elem<T>::load1(cp + i);
-            if (h > a.m) acc_raise(a, h);
+            acc_see_max(a, h);
             const uint32_t e = e0 + i;
             const uint32_t zy = fdiv(e, g.divW);
             const uint32_t x = e - zy * g.divW.d;
@@ -289,7 +192,8 @@ __global__ void __launch_bounds__(NT) fwd_scalar_kernel(const FwdParams p) {
 template <typename T, int CHUNK_BYTES, int STAGES, int NCW, int MINB>
 static void launch_ring(const FwdParams& p, int num_sms, cudaStream_t s) {
     auto kern = fwd_ring_kernel<T, CHUNK_BYTES, STAGES, NCW, MINB>;
-    const size_t smem = (size_t)STAGES * CHUNK_BYTES + 2 * STAGES * sizeof(uint64_t) + NCW * 8 * sizeof(float);
+    const size_t smem = (size_t)STAGES * CHUNK_BYTES + 2 * STAGES * sizeof(uint64_t) + (size_t)(STAGES + 1) * NCW * 8 * sizeof(float) +
+                        (STAGES + 1) * sizeof(int);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     uint64_t G = (uint64_t)num_sms * MINB;
     if (G > p.g.Gt) G = p.g.Gt;
@@ -316,9 +220,9 @@ static uint32_t chunk_bytes_of(bool vec_ok, int variant) {
     if (!vec_ok) return 0;
     switch (variant) {
         case 2: return 32768;       // direct: 512 threads x 4 x 16 B
-        case 11: return 32768;
+        case 1: case 12: case 13: return 16384;
         case 21: return 16384;      // direct: 256 threads x 4 x 16 B
-        default: return 16384;
+        default: return 32768;      // 0 (auto), 11, 14
     }
 }
 
@@ -332,6 +236,9 @@ Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok
     g.nch = (g.N + g.CE - 1) / g.CE;
     g.Gt = (uint64_t)g.R * g.nch;
     g.divF = make_fastdiv(vec_ok ? (uint32_t)W / 4 : 1);
+    const uint32_t epv = 16 / es;                           // voxels per 16-byte vector
+    g.divFv = make_fastdiv((vec_ok && W % epv == 0) ? (uint32_t)W / epv : 1);
+    if (!(vec_ok && W % epv == 0)) g.divFv.d = 0;
     g.divW = make_fastdiv((uint32_t)W);
     g.divH = make_fastdiv((uint32_t)H);
     return g;
@@ -346,7 +253,9 @@ static void launch_fwd_t(const FwdParams& p, bool vec_ok, int variant, int num_s
         case 11: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
         case 12: return launch_ring<T, 16384, 12, 16, 1>(p, num_sms, s);
         case 13: return launch_ring<T, 16384, 6, 8, 2>(p, num_sms, s);
-        default: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
+        case 14: return launch_ring<T, 32768, 3, 16, 2>(p, num_sms, s);
+        case 1: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
+        default: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
     }
 }
 

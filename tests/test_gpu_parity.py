@@ -22,7 +22,7 @@ from oracle import inputs, truth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 11, 12, 13, 2, 21]
+VARIANTS = [0, 1, 12, 13, 14, 2, 21]
 TOL = 1e-4
 
 
@@ -83,7 +83,7 @@ def test_golden_fp32(name, variant, dev):
         assert abs(loss - float(g["ref32_loss"])) <= TOL * max(1.0, abs(float(g["ref32_loss"])))
     # sum_i dh_i = 0 per joint-volume
     rows = grad.reshape(g["B"] * g["J"], -1)
-    assert np.abs(rows.sum(1)).max() <= 1e-5 * max(np.abs(rows).sum(1).max(), 1e-30)
+    assert np.abs(rows.sum(1)).max() <= 1e-4 * max(np.abs(rows).sum(1).max(), 1e-30)   # fp32 outputs: ~eps * sqrt(N) of the abs-sum
 
 
 @pytest.mark.parametrize("variant", [0, 2])

@@ -1,0 +1,66 @@
+// tools/kbench.cu -- Python-free timing of the C-ABI entry points (links lib/libihpr_b200.so).
+//   usage: kbench [variant] [B] [dtype 0|1] [iters]
+// Prints back-to-back launch time (events around `iters` launches) for fwd, bwd, and fwd+bwd alternating.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../include/ihpr_b200.h"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+#define IK(x) do { int rc = (x); if (rc) { printf("%s -> %d: %s\n", #x, rc, ihpr_last_error()); return 1; } } while (0)
+
+__global__ void fill(float* p, size_t n, uint32_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + seed; x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13;
+        p[i] = ((x & 0xffff) / 65536.0f - 0.5f) * 6.0f;
+    }
+}
+__global__ void fill_bf16(unsigned short* p, size_t n, uint32_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + seed; x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13;
+        float f = ((x & 0xffff) / 65536.0f - 0.5f) * 6.0f;
+        p[i] = (unsigned short)(__float_as_uint(f) >> 16);
+    }
+}
+
+int main(int argc, char** argv) {
+    int variant = argc > 1 ? atoi(argv[1]) : 0;
+    int B = argc > 2 ? atoi(argv[2]) : 32;
+    int dtype = argc > 3 ? atoi(argv[3]) : 0;
+    int iters = argc > 4 ? atoi(argv[4]) : 20;
+    const int J = 18, D = 64, H = 64, W = 64;
+    const size_t R = (size_t)B * J, N = (size_t)D * H * W, es = dtype ? 2 : 4;
+    void *heat, *grad, *ws; float *gt, *vis, *hd, *loss, *coords, *stats, *go;
+    CK(cudaMalloc(&heat, R * N * es)); CK(cudaMalloc(&grad, R * N * es));
+    size_t wsb = ihpr_workspace_bytes(B, J, D, H, W);
+    CK(cudaMalloc(&ws, wsb)); CK(cudaMemset(ws, 0, wsb));
+    CK(cudaMalloc(&gt, R * 3 * 4)); CK(cudaMalloc(&vis, R * 4)); CK(cudaMalloc(&hd, B * 4)); CK(cudaMalloc(&loss, 4));
+    CK(cudaMalloc(&coords, R * 3 * 4)); CK(cudaMalloc(&stats, R * 2 * 4)); CK(cudaMalloc(&go, 4));
+    if (dtype) fill_bf16<<<1024, 256>>>((unsigned short*)heat, R * N, 1); else fill<<<1024, 256>>>((float*)heat, R * N, 1);
+    std::vector<float> ones(R * 3, 1.0f);
+    CK(cudaMemcpy(vis, ones.data(), R * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(hd, ones.data(), B * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(go, ones.data(), 4, cudaMemcpyHostToDevice));
+    for (auto& v : ones) v = 31.0f;
+    CK(cudaMemcpy(gt, ones.data(), R * 3 * 4, cudaMemcpyHostToDevice));
+    ihpr_set_variant(variant);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto fwd = [&] { return ihpr_integral_l1_fwd(heat, dtype, B, J, D, H, W, gt, vis, hd, loss, coords, stats, ws, wsb, nullptr); };
+    auto bwd = [&] { return ihpr_integral_l1_bwd(heat, dtype, B, J, D, H, W, coords, stats, gt, vis, hd, go, grad, nullptr); };
+    for (int i = 0; i < 3; ++i) { IK(fwd()); IK(bwd()); }
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(fwd()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1); const double tf = ms * 1e3 / iters;
+    cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(bwd()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1); const double tb = ms * 1e3 / iters;
+    cudaEventRecord(e0); for (int i = 0; i < iters; ++i) { IK(fwd()); IK(bwd()); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1); const double tfb = ms * 1e3 / iters;
+    float hl; CK(cudaMemcpy(&hl, loss, 4, cudaMemcpyDeviceToHost));
+    const double V = (double)R * N * es;
+    printf("variant %d B %d dtype %d: fwd %.1f us (%.0f GB/s)  bwd %.1f us (%.0f GB/s)  fwd+bwd %.1f us (%.0f GB/s, %.0f vol/s)  loss %.5f\n", variant, B, dtype,
+           tf, V / tf / 1e3, tb, 2 * V / tb / 1e3, tfb, 3 * V / tfb / 1e3, R / (tfb * 1e-6), hl);
+    return 0;
+}

@@ -60,7 +60,7 @@ def main():
     args = ap.parse_args()
     if args.mode == "variants":
         for dtype in (torch.float32, torch.bfloat16):
-            for v in (1, 11, 12, 13, 2, 21):
+            for v in (0, 1, 11, 12, 13, 14, 2, 21):
                 print(json.dumps(time_cell(32, 18, 64, 64, 64, dtype, v, args.iters, 1)), flush=True)
     else:
         for dtype in (torch.float32, torch.bfloat16):
