@@ -15,8 +15,9 @@
  *   - stats are (B, J, 2) fp32: {m = max_i h_i, l = sum_i exp(h_i - m)}; logsumexp = m + ln l.
  *     The backward recomputes the softmax from heat + stats; the softmax is never materialised.
  *   - the caller owns every buffer, including the workspace (size from ihpr_workspace_bytes, must be
- *     zero-filled ONCE before first use; the kernels leave it zeroed again).  A workspace must not be
- *     shared by launches that may run concurrently (one per stream).
+ *     zero-filled ONCE before first use; the kernels leave its tickets zeroed again).  The ticket layout
+ *     depends on B*J: re-zero a workspace before reusing it with a different B*J.  A workspace must not
+ *     be shared by launches that may run concurrently (one per stream).
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
  *     except the *_host entry point, which is synchronous by contract.
  *   - return 0 on success, a negative IHPR_E* code otherwise; ihpr_last_error() gives the text
@@ -83,6 +84,20 @@ int ihpr_integral_l1_bwd(const void *heat, int dtype, int B, int J, int D, int H
                          const float *coords, const float *stats,
                          const float *gt, const float *vis, const float *have_depth,
                          const float *grad_out, void *grad_heat, void *stream);
+
+/* Training step in ONE launch: JointLocationLoss forward (as ihpr_integral_l1_fwd) plus d loss / d heat for an
+ * upstream gradient of 1, i.e. what main/train.py:67-71 (criterion + loss.backward()) produces.  Each
+ * joint-volume is streamed from HBM once and re-read from L2 (DRAM traffic 2 N s instead of 3 N s); needs a
+ * cooperative launch (partner CTAs of a joint-volume wait for each other).  Falls back to the two-kernel sequence
+ * for small batches and for shapes only the scalar kernels handle -- same results either way. */
+int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
+                             const float *gt, const float *vis, const float *have_depth,
+                             float *loss, float *coords, float *stats, void *grad_heat,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* grad_heat *= *grad_out (device scalar), a no-op launch when *grad_out == 1: turns the unit-gradient result of
+ * ihpr_integral_l1_fwd_bwd into autograd's answer for an arbitrary upstream gradient.  n = B*J*D*H*W elements. */
+int ihpr_scale_grad(void *grad_heat, int dtype, size_t n, const float *grad_out, void *stream);
 
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in

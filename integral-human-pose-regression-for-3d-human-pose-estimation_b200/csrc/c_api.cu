@@ -16,6 +16,7 @@ thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 std::atomic<int> g_variant{0};
 
+
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -40,13 +41,14 @@ int max_slots(int D, int H, int W) {
 }
 
 struct WsLayout {
-    size_t off_row_count, off_done, off_row_loss, off_partials, total;
+    size_t off_row_count, off_row_pass, off_done, off_row_loss, off_partials, total;
 };
 WsLayout ws_layout(int B, int J, int D, int H, int W) {
     const size_t R = (size_t)B * J;
     WsLayout l;
     l.off_row_count = 0;
-    l.off_done = R * sizeof(int);
+    l.off_row_pass = R * sizeof(int);
+    l.off_done = 2 * R * sizeof(int);
     l.off_row_loss = align_up(l.off_done + sizeof(int), 256);
     l.off_partials = align_up(l.off_row_loss + R * sizeof(float), 256);
     l.total = align_up(l.off_partials + R * (size_t)max_slots(D, H, W) * 8 * sizeof(float), 256);
@@ -119,12 +121,13 @@ int fwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
 }
 
 int bwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* coords, const float* stats, const float* grad_coords,
-               const float* gt, const float* vis, const float* hd, const float* grad_out, float loss_scale, void* grad_heat, void* stream) {
+               const float* gt, const float* vis, const float* hd, const float* grad_out, float loss_scale, void* grad_heat, void* stream,
+               float grad_out_const = 1.0f, bool allow_const = false) {
     g_launches = 0;
     int rc = check_shape(B, J, D, H, W, dtype);
     if (rc) return rc;
     if (!heat || !coords || !stats || !grad_heat) return fail(IHPR_EINVAL, "null heat / coords / stats / grad_heat");
-    if (!grad_coords && (!gt || !vis || !hd || !grad_out)) return fail(IHPR_EINVAL, "fused-loss backward needs gt, vis, have_depth and grad_out");
+    if (!grad_coords && (!gt || !vis || !hd || (!grad_out && !allow_const))) return fail(IHPR_EINVAL, "fused-loss backward needs gt, vis, have_depth and grad_out");
     int num_sms = 0;
     rc = check_device(heat, &num_sms);
     if (rc) return rc;
@@ -135,6 +138,7 @@ int bwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
     p.heat = heat; p.grad_heat = grad_heat; p.coords = coords; p.stats = stats;
     p.grad_coords = grad_coords; p.gt = gt; p.vis = vis; p.have_depth = hd; p.grad_out = grad_out;
     p.loss_scale = loss_scale;
+    p.grad_out_const = grad_out_const;
     ihpr::launch_bwd(p, dtype, v, variant, num_sms, static_cast<cudaStream_t>(stream));
     g_launches = 1;
     IHPR_CUDA(cudaGetLastError());
@@ -200,6 +204,68 @@ int ihpr_integral_l1_bwd(const void* heat, int dtype, int B, int J, int D, int H
                          const float* vis, const float* have_depth, const float* grad_out, void* grad_heat, void* stream) {
     const float scale = 1.0f / (3.0f * (float)B * (float)J);
     return bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, grad_out, scale, grad_heat, stream);
+}
+
+int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* gt, const float* vis, const float* have_depth,
+                             float* loss, float* coords, float* stats, void* grad_heat, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    int rc = check_shape(B, J, D, H, W, dtype);
+    if (rc) return rc;
+    if (!heat || !gt || !vis || !have_depth || !loss || !coords || !stats || !grad_heat || !workspace)
+        return fail(IHPR_EINVAL, "null argument");
+    const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
+    const int variant = g_variant.load(std::memory_order_relaxed);
+    const float scale = 1.0f / (3.0f * (float)B * (float)J);
+    ihpr::Geometry g = ihpr::make_geometry(B, J, D, H, W, dtype, v, 0);
+    int num_sms = 0;
+    rc = check_device(heat, &num_sms);
+    if (rc) return rc;
+    const int S = v ? ihpr::fused_split(g, dtype) : 1;
+    // the fused kernel wants enough joint-volumes to keep every CTA group busy for a few rounds; otherwise (tiny
+    // batches: everything fits in L2 anyway) or on the scalar path run K1 then K2
+    const bool fused = v && variant != 9 && (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S;
+    if (!fused) {
+        rc = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        rc = bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, nullptr, scale, grad_heat, stream, 1.0f, true);
+        if (rc) return rc;
+        g_launches = 2;
+        return IHPR_OK;
+    }
+    const WsLayout l = ws_layout(B, J, D, H, W);
+    if (workspace_bytes < l.total) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, l.total);
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    ihpr::FusedParams p;
+    p.f.g = g;
+    p.f.heat = heat; p.f.coords = coords; p.f.stats = stats;
+    p.f.gt = gt; p.f.vis = vis; p.f.have_depth = have_depth; p.f.loss = loss;
+    char* w8 = static_cast<char*>(workspace);
+    p.f.row_count = reinterpret_cast<int*>(w8 + l.off_row_count);
+    p.row_pass = reinterpret_cast<int*>(w8 + l.off_row_pass);
+    p.f.done_rows = reinterpret_cast<int*>(w8 + l.off_done);
+    p.f.row_loss = reinterpret_cast<float*>(w8 + l.off_row_loss);
+    p.f.partials = reinterpret_cast<float*>(w8 + l.off_partials);
+    p.f.maxslots = max_slots(D, H, W);
+    p.grad_heat = grad_heat;
+    p.S = S;
+    p.loss_scale = scale;
+    IHPR_CUDA(ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream)));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+int ihpr_scale_grad(void* grad_heat, int dtype, size_t n, const float* grad_out, void* stream) {
+    g_launches = 0;
+    if (!grad_heat || !grad_out) return fail(IHPR_EINVAL, "null argument");
+    if (dtype != IHPR_F32 && dtype != IHPR_BF16) return fail(IHPR_EINVAL, "dtype %d is neither IHPR_F32 nor IHPR_BF16", dtype);
+    int num_sms = 0;
+    int rc = check_device(grad_heat, &num_sms);
+    if (rc) return rc;
+    ihpr::launch_scale(grad_heat, n, dtype, ((uintptr_t)grad_heat & 15) == 0, grad_out, num_sms, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
 }
 
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ihpr {
 
@@ -151,7 +152,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef IHPR_DEBUG_HANG
+// debug build: a wait that spins "forever" reports who is stuck on what and traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+    for (unsigned long long spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1ull << 22)) {
+            printf("HANG cta %d warp %d lane %d tag %d parity %u\n", blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, tag, parity);
+            __trap();
+        }
+    }
+}
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+    (void)tag;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -160,6 +177,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -271,8 +289,17 @@ struct BwdParams {
     const float* gt;        // fused loss inputs
     const float* vis;
     const float* have_depth;
-    const float* grad_out;  // device scalar
+    const float* grad_out;  // device scalar, or null: use grad_out_const
+    float grad_out_const;
     float loss_scale;       // 1 / (3 * B_total * J): loss.py:50,52 (B_total may exceed this launch's slice)
+};
+
+struct FusedParams {
+    FwdParams f;            // gt / vis / have_depth / loss are mandatory here
+    void* grad_heat;        // d loss / d heat for upstream gradient 1
+    int* row_pass;          // (R) second ticket that re-arms row_count
+    int S;                  // CTAs per joint-volume
+    float loss_scale;       // 1 / (3 * B * J)
 };
 
 // chunk range of persistent CTA `cta` of G: [cta*Gt/G, (cta+1)*Gt/G)
@@ -283,5 +310,8 @@ __device__ __forceinline__ uint32_t owner_of(uint64_t g, uint64_t Gt, uint32_t G
 void launch_fwd(const FwdParams& p, int dtype, bool vec_ok, int variant, int num_sms, cudaStream_t s);
 void launch_bwd(const BwdParams& p, int dtype, bool vec_ok, int variant, int num_sms, cudaStream_t s);
 Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok, int variant);
+int fused_split(const Geometry& g, int dtype);
+cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s);
+void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
 
 }  // namespace ihpr

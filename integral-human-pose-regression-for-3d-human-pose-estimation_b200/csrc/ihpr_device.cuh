@@ -240,7 +240,7 @@ __device__ __forceinline__ RowK load_row(const BwdParams& p, uint32_t r) {
         gy = __ldg(p.grad_coords + 3 * (size_t)r + 1);
         gz = __ldg(p.grad_coords + 3 * (size_t)r + 2);
     } else {
-        const float s = __ldg(p.grad_out) * __ldg(p.vis + r) * p.loss_scale;
+        const float s = (p.grad_out ? __ldg(p.grad_out) : p.grad_out_const) * __ldg(p.vis + r) * p.loss_scale;
         gx = s * sgn(k.cx - __ldg(p.gt + 3 * (size_t)r));
         gy = s * sgn(k.cy - __ldg(p.gt + 3 * (size_t)r + 1));
         gz = s * sgn(k.cz - __ldg(p.gt + 3 * (size_t)r + 2)) * __ldg(p.have_depth + r / p.g.J);

@@ -3,6 +3,7 @@
 PyTorch is plumbing here (device memory, the current stream, autograd bookkeeping); all arithmetic
 runs in lib/libihpr_b200.so.  Semantics follow /root/reference/common/nets/loss.py:13-52.
 """
+import os
 import threading
 
 import torch
@@ -11,7 +12,7 @@ from . import _lib
 from ._lib import IHPR_BF16, IHPR_F32, IhprError, check, lib
 
 _ws_lock = threading.Lock()
-_ws_cache = {}      # (device index, stream handle) -> zero-initialised uint8 workspace
+_ws_cache = {}      # (device index, stream handle, B*J) -> zero-initialised uint8 workspace
 
 
 def _dtype_code(t):
@@ -39,8 +40,10 @@ def _shape(heat, joint_num):
     return B, C // joint_num, H, W
 
 
-def _workspace(dev, stream, nbytes):
-    key = (dev.index, stream)
+def _workspace(dev, stream, nbytes, rows):
+    # the kernels leave the workspace's tickets zeroed, but WHERE the tickets live depends on B*J
+    # (include/ihpr_b200.h): one workspace per (device, stream, B*J)
+    key = (dev.index, stream, rows)
     with _ws_lock:
         ws = _ws_cache.get(key)
         if ws is None or ws.numel() < nbytes:
@@ -68,7 +71,7 @@ def _fwd(heat, joint_num, targets=None):
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         nbytes = L.ihpr_workspace_bytes(B, joint_num, D, H, W)
-        ws = _workspace(dev, stream, nbytes)
+        ws = _workspace(dev, stream, nbytes, B * joint_num)
         coords = torch.empty((B, joint_num, 3), dtype=torch.float32, device=dev)
         stats = torch.empty((B, joint_num, 2), dtype=torch.float32, device=dev)
         if targets is None:
@@ -132,6 +135,53 @@ class _IntegralL1(torch.autograd.Function):
         return grad_heat, None, None, None
 
 
+class _IntegralL1Fused(torch.autograd.Function):
+    """Loss and d loss / d heat in one launch (K5); backward only rescales by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, heat, gt, vis, hd):
+        heat = heat.contiguous()
+        J = gt.shape[1]
+        B, D, H, W = _shape(heat, J)
+        dev = heat.device
+        L = lib()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = _workspace(dev, stream, L.ihpr_workspace_bytes(B, J, D, H, W), B * J)
+            coords = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+            stats = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            grad_unit = torch.empty_like(heat)
+            check(L.ihpr_integral_l1_fwd_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, gt.data_ptr(), vis.data_ptr(),
+                                             hd.data_ptr(), loss.data_ptr(), coords.data_ptr(), stats.data_ptr(),
+                                             grad_unit.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        ctx.joint_num = J
+        ctx.grad_unit = grad_unit           # consumed (scaled in place) by the first backward
+        ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
+        ctx.mark_non_differentiable(coords)
+        return loss, coords
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_coords):
+        heat, coords, stats, gt, vis, hd = ctx.saved_tensors
+        J = ctx.joint_num
+        B, D, H, W = _shape(heat, J)
+        go = grad_loss.to(torch.float32).contiguous()
+        L = lib()
+        with torch.cuda.device(heat.device):
+            stream = torch.cuda.current_stream(heat.device).cuda_stream
+            grad_heat = ctx.grad_unit
+            if grad_heat is not None:
+                ctx.grad_unit = None
+                check(L.ihpr_scale_grad(grad_heat.data_ptr(), _dtype_code(heat), grad_heat.numel(), go.data_ptr(), stream))
+            else:                           # a second backward through a retained graph: recompute (K2)
+                grad_heat = torch.empty_like(heat)
+                check(L.ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
+                                             stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
+                                             go.data_ptr(), grad_heat.data_ptr(), stream))
+        return grad_heat, None, None, None
+
+
 def _normalise(heat):
     # fp16 / fp64 heatmaps are computed in fp32 (the cast is differentiable torch plumbing)
     if heat.dtype not in (torch.float32, torch.bfloat16):
@@ -150,8 +200,12 @@ def soft_argmax(heatmaps, joint_num):
     return _SoftArgmax3D.apply(_normalise(heatmaps), int(joint_num))
 
 
-def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords=False):
-    """Fused soft-argmax + L1 coordinate loss (loss.py:36-52): one launch forward, one backward."""
+def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords=False, fused_backward=None):
+    """Fused soft-argmax + L1 coordinate loss (loss.py:36-52).
+
+    fused_backward=True (default when the heatmaps require grad; IHPR_FUSED=0 disables): the forward launch also
+    produces d loss / d heat (K5, DRAM traffic 2V) and backward() only applies the upstream gradient.
+    fused_backward=False: one forward launch (K1) and one recomputing backward launch (K2), traffic 3V."""
     _require_cuda(heatmap_out, "heatmap_out")
     if gt_coord.dim() != 3 or gt_coord.shape[2] != 3:
         raise ValueError("gt_coord must be (B, J, 3), got %s" % (tuple(gt_coord.shape),))
@@ -163,7 +217,13 @@ def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords
     gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
     vis = _f32(gt_vis, dev, (B, J), "gt_vis")
     hd = _f32(gt_have_depth, dev, (B, 1), "gt_have_depth")
-    loss, coords = _IntegralL1.apply(_normalise(heatmap_out), gt, vis, hd)
+    if fused_backward is None:
+        fused_backward = os.environ.get("IHPR_FUSED", "1") != "0"
+    heat = _normalise(heatmap_out)
+    if fused_backward and heat.requires_grad and torch.is_grad_enabled():
+        loss, coords = _IntegralL1Fused.apply(heat, gt, vis, hd)
+    else:
+        loss, coords = _IntegralL1.apply(heat, gt, vis, hd)
     return (loss, coords) if return_coords else loss
 
 

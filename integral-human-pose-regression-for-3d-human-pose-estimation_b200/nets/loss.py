@@ -42,8 +42,10 @@ def soft_argmax(heatmaps, joint_num):
 
 
 class JointLocationLoss(nn.Module):
-    def __init__(self):
+    def __init__(self, fused_backward=None):
+        """fused_backward: None = library default (on), see functional.integral_l1_loss."""
         super(JointLocationLoss, self).__init__()
+        self.fused_backward = fused_backward
 
     def forward(self, heatmap_out, gt_coord, gt_vis, gt_have_depth):
         joint_num = gt_coord.shape[1]                                    # loss.py:42
@@ -51,7 +53,7 @@ class JointLocationLoss(nn.Module):
         _assert_no_grad(gt_vis)
         _assert_no_grad(gt_have_depth)
         _check_cfg(heatmap_out, joint_num)
-        return integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth)
+        return integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, fused_backward=self.fused_backward)
 
 
 class JointMSELoss(nn.Module):

@@ -39,12 +39,12 @@ def _reset_variant():
     ihpr_b200.set_variant(0)
 
 
-def run_ours(g_heat, gt, vis, hd, dev, dtype=torch.float32):
+def run_ours(g_heat, gt, vis, hd, dev, dtype=torch.float32, fused=False, grad_out=None):
     import ihpr_b200
     h = torch.from_numpy(g_heat).to(dev).to(dtype).requires_grad_(True)
     tg, tv, th = (torch.from_numpy(a).to(dev) for a in (gt, vis, hd))
-    loss, coords = ihpr_b200.integral_l1_loss(h, tg, tv, th, return_coords=True)
-    loss.backward()
+    loss, coords = ihpr_b200.integral_l1_loss(h, tg, tv, th, return_coords=True, fused_backward=fused)
+    (loss if grad_out is None else loss * grad_out).backward()
     torch.cuda.synchronize()
     return loss.item(), coords.cpu().numpy().astype(np.float64), h.grad.float().cpu().numpy().astype(np.float64)
 
@@ -114,6 +114,55 @@ def test_oracle_seeded_shapes(shape, dist, dev):
     assert coord_err(coords, c64) <= TOL
     assert abs(loss - l64) <= TOL * max(1.0, abs(l64))
     assert grad_err(grad, g64) <= TOL
+
+
+@pytest.mark.parametrize("case", [
+    # (B, J, D, H, W, dtype): enough joint-volumes that ihpr_integral_l1_fwd_bwd takes the single-launch path (K5)
+    (20, 16, 8, 8, 8, torch.float32),          # S = 1 (a joint-volume is one unit), partial chunks
+    (9, 17, 32, 64, 64, torch.float32),        # S = 2 (512 KiB joint-volumes)
+    (10, 18, 64, 64, 64, torch.float32),       # S = 4 (1 MiB joint-volumes), the headline geometry
+    (10, 18, 64, 64, 64, torch.bfloat16),      # S = 2 in bf16
+    (40, 8, 3, 5, 12, torch.float32),          # generic (non-fast) vector path inside K5
+    (40, 8, 3, 5, 9, torch.float32),           # scalar shapes: falls back to K1 + K2
+])
+def test_fused_forward_backward(case, dev):
+    import ihpr_b200
+    B, J, D, H, W, dtype = case
+    heat = inputs.make_heat("randn3", B, J, D, H, W, seed=7)
+    if dtype == torch.bfloat16:
+        heat = torch.from_numpy(heat).to(torch.bfloat16).float().numpy()
+    gt, vis, hd = inputs.make_targets(B, J, D, H, W, seed=7, vis_mode="rand", hd_mode="alt")
+    l64, c64, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd, grad_out=1.75)
+    loss, coords, grad = run_ours(heat, gt, vis, hd, dev, dtype=dtype, fused=True, grad_out=1.75)
+    assert coord_err(coords, c64) <= TOL and abs(loss - l64) <= TOL * max(1.0, abs(l64))
+    if dtype == torch.float32:
+        assert grad_err(grad, g64) <= TOL
+    else:       # bf16 gradient, rounded once by K5 and once more by the in-place scale
+        assert (np.abs(grad - g64) <= 2.0 ** -7 * np.abs(g64) + 1e-4 * np.abs(g64).max()).all()
+    # unfused path on the same inputs agrees to rounding
+    loss_u, coords_u, grad_u = run_ours(heat, gt, vis, hd, dev, dtype=dtype, fused=False, grad_out=1.75)
+    assert np.abs(coords - coords_u).max() <= 1e-3 and abs(loss - loss_u) <= 1e-5
+    assert np.abs(grad - grad_u).max() <= (1e-5 if dtype == torch.float32 else 2.0 ** -6) * np.abs(g64).max()
+
+
+def test_fused_is_deterministic_and_retained_graph_backward(dev):
+    import ihpr_b200
+    B, J, D, H, W = 10, 18, 64, 64, 64
+    gen = torch.Generator(device=dev).manual_seed(3)
+    h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
+    gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 3, "rand", "alt"))
+    outs = []
+    for _ in range(3):
+        h.grad = None
+        loss, coords = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True, fused_backward=True)
+        loss.backward(retain_graph=True)
+        outs.append((loss.detach().clone(), coords.clone(), h.grad.clone()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+    # second backward through the retained graph recomputes with K2 and must give the same gradient again
+    h.grad = None
+    loss.backward()
+    assert (h.grad - outs[0][2]).abs().max().item() <= 1e-6 * outs[0][2].abs().max().item()
 
 
 def test_soft_argmax_only_and_custom_grad(dev):

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#include <time.h>
+#include <unistd.h>
 #include "../include/ihpr_b200.h"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
@@ -49,8 +51,21 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto fwd = [&] { return ihpr_integral_l1_fwd(heat, dtype, B, J, D, H, W, gt, vis, hd, loss, coords, stats, ws, wsb, nullptr); };
     auto bwd = [&] { return ihpr_integral_l1_bwd(heat, dtype, B, J, D, H, W, coords, stats, gt, vis, hd, go, grad, nullptr); };
+    const bool verbose = getenv("KB_VERBOSE") != nullptr;
+    const bool only_fused = getenv("KB_ONLY_FUSED") != nullptr;
+    auto fused = [&] { return ihpr_integral_l1_fwd_bwd(heat, dtype, B, J, D, H, W, gt, vis, hd, loss, coords, stats, grad, ws, wsb, nullptr); };
+    if (only_fused) {
+        for (int i = 0; i < iters; ++i) {
+            IK(fused());
+            if (verbose) { printf("fused launch %d enqueued (%d kernels)\n", i, ihpr_last_launch_count()); fflush(stdout); }
+            CK(cudaDeviceSynchronize());
+            if (verbose) { printf("fused launch %d done\n", i); fflush(stdout); }
+        }
+        return 0;
+    }
     for (int i = 0; i < 3; ++i) { IK(fwd()); IK(bwd()); }
     CK(cudaDeviceSynchronize());
+    if (verbose) { printf("K1/K2 warm-up done\n"); fflush(stdout); }
     float ms;
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(fwd()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tf = ms * 1e3 / iters;
@@ -58,8 +73,15 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1); const double tb = ms * 1e3 / iters;
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) { IK(fwd()); IK(bwd()); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tfb = ms * 1e3 / iters;
+    if (verbose) { printf("K1/K2 timing done\n"); fflush(stdout); }
+    for (int i = 0; i < 3; ++i) IK(fused());
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(fused()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1); const double tfu = ms * 1e3 / iters;
     float hl; CK(cudaMemcpy(&hl, loss, 4, cudaMemcpyDeviceToHost));
     const double V = (double)R * N * es;
+    printf("variant %d B %d dtype %d: FUSED one-launch fwd+bwd %.1f us (%d launch; %.0f GB/s as 3V, %.0f GB/s as 2V, %.0f vol/s)\n", variant, B, dtype, tfu,
+           ihpr_last_launch_count(), 3 * (double)R * N * es / tfu / 1e3, 2 * (double)R * N * es / tfu / 1e3, R / (tfu * 1e-6));
     printf("variant %d B %d dtype %d: fwd %.1f us (%.0f GB/s)  bwd %.1f us (%.0f GB/s)  fwd+bwd %.1f us (%.0f GB/s, %.0f vol/s)  loss %.5f\n", variant, B, dtype,
            tf, V / tf / 1e3, tb, 2 * V / tb / 1e3, tfb, 3 * V / tfb / 1e3, R / (tfb * 1e-6), hl);
     return 0;
