@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -41,17 +42,18 @@ int max_slots(int D, int H, int W) {
 }
 
 struct WsLayout {
-    size_t off_row_count, off_row_pass, off_done, off_row_loss, off_partials, total;
+    size_t off_row_count, off_done, off_epoch, off_row_loss, off_partials, off_xslots, total;
 };
 WsLayout ws_layout(int B, int J, int D, int H, int W) {
     const size_t R = (size_t)B * J;
     WsLayout l;
     l.off_row_count = 0;
-    l.off_row_pass = R * sizeof(int);
-    l.off_done = 2 * R * sizeof(int);
-    l.off_row_loss = align_up(l.off_done + sizeof(int), 256);
+    l.off_done = R * sizeof(int);
+    l.off_epoch = l.off_done + sizeof(int);
+    l.off_row_loss = align_up(l.off_epoch + sizeof(int), 256);
     l.off_partials = align_up(l.off_row_loss + R * sizeof(float), 256);
-    l.total = align_up(l.off_partials + R * (size_t)max_slots(D, H, W) * 8 * sizeof(float), 256);
+    l.off_xslots = align_up(l.off_partials + R * (size_t)max_slots(D, H, W) * 8 * sizeof(float), 256);
+    l.total = align_up(l.off_xslots + R * (size_t)ihpr::kMaxSplit * 8 * sizeof(uint2), 256);
     return l;
 }
 
@@ -241,7 +243,8 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.f.gt = gt; p.f.vis = vis; p.f.have_depth = have_depth; p.f.loss = loss;
     char* w8 = static_cast<char*>(workspace);
     p.f.row_count = reinterpret_cast<int*>(w8 + l.off_row_count);
-    p.row_pass = reinterpret_cast<int*>(w8 + l.off_row_pass);
+    p.xslots = reinterpret_cast<uint2*>(w8 + l.off_xslots);
+    p.epoch = reinterpret_cast<int*>(w8 + l.off_epoch);
     p.f.done_rows = reinterpret_cast<int*>(w8 + l.off_done);
     p.f.row_loss = reinterpret_cast<float*>(w8 + l.off_row_loss);
     p.f.partials = reinterpret_cast<float*>(w8 + l.off_partials);
@@ -249,6 +252,7 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.grad_heat = grad_heat;
     p.S = S;
     p.loss_scale = scale;
+    p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;
     IHPR_CUDA(ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream)));
     g_launches = 1;
     IHPR_CUDA(cudaGetLastError());

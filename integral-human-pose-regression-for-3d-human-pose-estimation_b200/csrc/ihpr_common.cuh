@@ -14,6 +14,7 @@ namespace ihpr {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kGridCap = 2048;          // upper bound on persistent CTAs (workspace sizing)
+constexpr int kMaxSplit = 16;           // K5: at most this many CTAs share one joint-volume
 constexpr int kMinChunkElems = 2048;    // every kernel config streams chunks of >= this many voxels
 
 // ---------------------------------------------------------------------------------------------
@@ -297,9 +298,11 @@ struct BwdParams {
 struct FusedParams {
     FwdParams f;            // gt / vis / have_depth / loss are mandatory here
     void* grad_heat;        // d loss / d heat for upstream gradient 1
-    int* row_pass;          // (R) second ticket that re-arms row_count
+    uint2* xslots;          // (R, kMaxSplit, 8) {value, tag} pairs: partials traded between the S CTAs of a volume
+    int* epoch;             // launch counter in the workspace; tag = epoch + 1
     int S;                  // CTAs per joint-volume
     float loss_scale;       // 1 / (3 * B * J)
+    int debug_no_exchange;  // timing experiments only (IHPR_DEBUG_NOXCHG=1): skip the cross-CTA trade, WRONG results
 };
 
 // chunk range of persistent CTA `cta` of G: [cta*Gt/G, (cta+1)*Gt/G)

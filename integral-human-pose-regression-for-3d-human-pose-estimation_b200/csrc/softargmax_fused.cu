@@ -3,8 +3,8 @@
 // The reference's training step runs JointLocationLoss forward, then autograd backward
 // (/root/reference/main/train.py:67-71): 11-15 V of DRAM traffic.  K1 + K2 bring that to the algorithmic
 // 3 V (read, re-read, write).  K5 removes the re-read: a joint-volume is split over S persistent CTAs
-// (S*unit = N*s bytes, unit <= 256 KiB so that the units all CTAs have in flight, 148 * 256 KiB = 37 MiB,
-// stay resident in the 126 MB L2 -- tools/l2reuse.cu measures where that stops working); each CTA
+// (S*unit = N*s bytes; the units all CTAs hold between their two passes, 148 * 256 KiB = 37 MiB, stay resident in the
+// 126 MB L2 -- tools/l2reuse.cu measures where that stops working); each CTA
 //   pass 1  streams its unit from HBM through the TMA ring (L2 evict_last) and accumulates (m, l, sx, sy, sz),
 //   merge   publishes the partial, waits for its S-1 partner CTAs (all co-resident: cooperative launch),
 //           merges the S slots in slot order, forms coords, the loss term and g = dLoss/dcoords (loss.py:49-52
@@ -12,7 +12,7 @@
 //   pass 2  streams the same unit again -- now L2 hits (evict_first) -- and writes grad_heat.
 // DRAM traffic: read V + write V.  The producer warp never stops: pass-2 chunks of this unit and pass-1 chunks
 // of the next one are already in the ring while the consumers exchange partials.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "ihpr_device.cuh"
 
@@ -23,28 +23,39 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+
+// Roles: warp 0 = TMA producer, warps 1..DEPTH+1 = exchangers (merge warp partials, trades CTA partials with the partner
+// CTAs, form the per-volume backward constants and write coords / stats / loss term), the last NCW warps = consumers.
+// The stream is software-pipelined by DEPTH units: consumers run pass1(u0..u_{DEPTH-1}), then alternate
+// pass1(u+DEPTH), pass2(u), so the exchange of unit u has DEPTH * (pass1 + pass2) - pass2 of time before its result
+// is needed; DEPTH + 1 units per CTA are live in L2.
+//
+// Exchange protocol (no fences, no atomics, one L2 round trip after the slowest partner): every CTA of the group
+// stores its 6-word partial as six 8-byte {value, tag} pairs into its slot of the joint-volume's exchange row; every
+// exchanger polls all S slots until each pair carries this launch's tag (an 8-byte store is single-copy atomic, so a
+// matching tag proves the value next to it).  tag = launch epoch + 1; the epoch lives in the workspace and is bumped
+// by the last CTA to finish.
+__device__ __forceinline__ void st_pair(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
 }
 
-// Roles: warp 0 = TMA producer, warp 1 = exchanger (merges warp partials, trades CTA partials with the partner
-// CTAs, forms the per-volume backward constants and writes coords / stats / loss), warps 2.. = NCW consumers.
-// The stream is software-pipelined by one unit: consumers run  pass1(u0), pass1(u1), pass2(u0), pass1(u2),
-// pass2(u1), ...  so the exchange of unit i happens while they are busy with pass 1 of unit i+1 and never
-// stalls them; at most two units per CTA are live in L2.
-template <typename T, int CHUNK_BYTES, int STAGES, int NCW>
-__global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const FusedParams p) {
+template <typename T, int CHUNK_BYTES, int STAGES, int NCW, int DEPTH>
+__global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(const FusedParams p) {
+    constexpr int NB = DEPTH + 1;               // units in flight between pass 1 and pass 2 = exchanger warps
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * CHUNK_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* part_full = empty + STAGES;       // [2] consumers -> exchanger: NCW warp partials are in pbuf[par]
-    uint64_t* rk_full = part_full + 2;          // [2] exchanger -> consumers: rowk[par] is valid
-    uint64_t* rk_empty = rk_full + 2;           // [2] consumers -> exchanger: rowk[par] has been read by all
-    float(*pbuf)[8] = reinterpret_cast<float(*)[8]>(rk_empty + 2);      // [2][NCW][8]
-    volatile float* rowk = reinterpret_cast<volatile float*>(pbuf + 2 * NCW);   // [2][8]
+    uint64_t* part_full = empty + STAGES;       // [NB] consumers -> exchanger: NCW warp partials are in pbuf[b]
+    uint64_t* rk_full = part_full + NB;         // [NB] exchanger -> consumers: rowk[b] is valid
+    uint64_t* rk_empty = rk_full + NB;          // [NB] consumers -> exchanger: rowk[b] has been read by all
+    float(*pbuf)[8] = reinterpret_cast<float(*)[8]>(rk_empty + NB);             // [NB][NCW][8]
+    volatile float* rowk = reinterpret_cast<volatile float*>(pbuf + NB * NCW);  // [NB][8]
 
     const Geometry& g = p.f.g;
     const int S = p.S;
@@ -56,7 +67,7 @@ __global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const Fuse
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
-        for (int b = 0; b < 2; ++b) { mbar_init(part_full + b, NCW); mbar_init(rk_full + b, 1); mbar_init(rk_empty + b, NCW); }
+        for (int b = 0; b < NB; ++b) { mbar_init(part_full + b, NCW); mbar_init(rk_full + b, 1); mbar_init(rk_empty + b, NCW); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -78,96 +89,109 @@ __global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const Fuse
                     bulk_g2s(ring + (size_t)s * CHUNK_BYTES, src + ((size_t)r * g.N + e0) * sizeof(T), bytes, full + s, pass ? pol_drop : pol_keep);
                 }
             };
-            if (nunits) issue(0, 0);
+            for (uint32_t u = 0; u < (uint32_t)DEPTH && u < nunits; ++u) issue(u, 0);
             for (uint32_t u = 0; u < nunits; ++u) {
-                if (u + 1 < nunits) issue(u + 1, 0);
+                if (u + DEPTH < nunits) issue(u + DEPTH, 0);
                 issue(u, 1);
             }
         }
         return;
     }
 
-    if (warp == 1) {
-        // ================= exchanger =================
-        for (uint32_t u = 0; u < nunits; ++u) {
+    if (warp <= NB) {
+        // ================= exchangers: warp 1 + b serves the units u = b (mod NB) =================
+        // (one exchange costs a few loaded-L2 round trips, ~5 us, more than a unit takes to stream: NB of them run
+        //  concurrently so that the exchange THROUGHPUT keeps up; the DEPTH-unit look-ahead hides the latency)
+        const uint32_t tag = (uint32_t)__ldcg(p.epoch) + 1u;
+        const uint32_t b = warp - 1;
+        for (uint32_t u = b; u < nunits; u += NB) {
             const uint32_t r = group + u * ngroups;
-            const uint32_t par = u & 1, ph = (u >> 1) & 1;
+            const uint32_t ph = (u / NB) & 1;
             // targets of this volume: fetched before the wait so their latency hides behind pass 1
             const float v = __ldg(p.f.vis + r), hd = __ldg(p.f.have_depth + r / g.J);
             const float gtx = __ldg(p.f.gt + 3 * (size_t)r), gty = __ldg(p.f.gt + 3 * (size_t)r + 1), gtz = __ldg(p.f.gt + 3 * (size_t)r + 2);
-            if (lane == 0) mbar_wait(part_full + par, ph, 2);
+            if (lane == 0) mbar_wait(part_full + b, ph, 2);
             __syncwarp();
             Acc t;
             t.reset();
-            if (lane < NCW) t = partial_from_smem(pbuf[par * NCW + lane]);
+            if (lane < NCW) t = partial_from_smem(pbuf[b * NCW + lane]);
             t = acc_warp_merge(t);
-            if (S > 1) {
-                float* slots = p.f.partials + (size_t)r * p.f.maxslots * 8;
-                if (lane == 0) {
-                    partial_to_global(slots + q * 8, t);
-                    __threadfence();
-                    atomicAdd(p.f.row_count + r, 1);
-                    #ifdef IHPR_DEBUG_HANG
-                    for (unsigned long long spins = 0; ld_acquire(p.f.row_count + r) < S; ++spins) {
-                        if (spins > (1ull << 20)) { printf("HANG cta %d exchange volume %u count %d of %d\n", blockIdx.x, r, ld_acquire(p.f.row_count + r), S); __trap(); }
-                        __nanosleep(32);
+            if (S > 1 && !p.debug_no_exchange) {
+                uint2* row = p.xslots + (size_t)r * (kMaxSplit * 8);
+                if (lane < 6) {
+                    const float w = lane == 0 ? t.m : lane == 1 ? t.l : lane == 2 ? t.sx : lane == 3 ? t.sy : lane == 4 ? t.sz : t.mx;
+                    st_pair(row + q * 8 + lane, w, tag);
+                }
+                t.reset();
+                if (lane < S) {
+                    // poll ONE pair per partner (keeps the polling traffic of 4 x 144 exchanger warps small), then
+                    // fetch the other five and re-check their tags: stores of different lanes are not ordered
+                    const uint2* slot = row + lane * 8;
+                    uint2 w[6];
+                    for (;;) {
+                        w[0] = ld_pair(slot);
+                        if (w[0].y == tag) break;
+                        __nanosleep(100);
                     }
-#else
-                    while (ld_acquire(p.f.row_count + r) < S) __nanosleep(32);
-#endif
+                    for (;;) {
+#pragma unroll
+                        for (int i = 1; i < 6; ++i) w[i] = ld_pair(slot + i);
+                        bool ok = true;
+#pragma unroll
+                        for (int i = 1; i < 6; ++i) ok = ok && (w[i].y == tag);
+                        if (ok) break;
+                    }
+                    t.m = __uint_as_float(w[0].x); t.l = __uint_as_float(w[1].x); t.sx = __uint_as_float(w[2].x);
+                    t.sy = __uint_as_float(w[3].x); t.sz = __uint_as_float(w[4].x); t.mx = __uint_as_float(w[5].x);
+                    t.c = safe_c(t.m); t.lim = t.m + kRebaseSlack;
                 }
                 __syncwarp();
-                __threadfence();
-                t.reset();
-                if (lane < S) t = partial_from_global(slots + lane * 8);
                 t = acc_warp_merge(t);          // same instruction sequence in all S CTAs: identical bits
             }
             const float inv = 1.0f / t.l;
             const float cx = t.sx * inv, cy = t.sy * inv, cz = t.sz * inv;
-            // consumers are done with the constants of unit u-2.  One lane waits and the warp re-converges before
+            // consumers are done with the constants of unit u-NB.  One lane waits and the warp re-converges before
             // rk_full is signalled: a lane that polled rk_empty only after the consumers (released by rk_full) had
             // already completed its NEXT phase would wait on the wrong parity forever.
-            if (lane == 0) mbar_wait(rk_empty + par, ph ^ 1, 3);
+            if (lane == 0) mbar_wait(rk_empty + b, ph ^ 1, 3);
             __syncwarp();
             if (lane == 0) {
                 const float sc = v * p.loss_scale * inv;           // upstream gradient 1, pre-divided by l
-                volatile float* rk = rowk + par * 8;
+                volatile float* rk = rowk + b * 8;
                 rk[0] = t.c;
                 rk[1] = sc * sgn(cx - gtx);
                 rk[2] = sc * sgn(cy - gty);
                 rk[3] = sc * sgn(cz - gtz) * hd;
                 rk[4] = cx; rk[5] = cy; rk[6] = cz;
-                mbar_arrive(rk_full + par);
+                mbar_arrive(rk_full + b);
             }
-            // ---- off the critical path: re-arm the ticket, outputs, loss
-            if (S > 1 && lane == 0) {
-                if (atomicAdd(p.row_pass + r, 1) == S - 1) { p.f.row_count[r] = 0; p.row_pass[r] = 0; }
-            }
-            if (q == 0) {
-                int t2 = 0;
-                if (lane == 0) {
-                    p.f.coords[3 * (size_t)r + 0] = cx;
-                    p.f.coords[3 * (size_t)r + 1] = cy;
-                    p.f.coords[3 * (size_t)r + 2] = cz;
-                    if (p.f.stats) {
-                        const float f = (t.m == -INFINITY) ? 0.f : ex2(t.c - safe_c(t.mx));
-                        p.f.stats[2 * (size_t)r] = t.mx;
-                        p.f.stats[2 * (size_t)r + 1] = t.l * f;
-                    }
-                    __stcg(p.f.row_loss + r, (fabsf(cx - gtx) * v + fabsf(cy - gty) * v + fabsf(cz - gtz) * v * hd) / 3.f);
-                    __threadfence();
-                    t2 = atomicAdd(p.f.done_rows, 1);
+            // ---- off the critical path: outputs of this joint-volume (plain stores; published by the final ticket)
+            if (q == 0 && lane == 0) {
+                p.f.coords[3 * (size_t)r + 0] = cx;
+                p.f.coords[3 * (size_t)r + 1] = cy;
+                p.f.coords[3 * (size_t)r + 2] = cz;
+                if (p.f.stats) {
+                    const float f = (t.m == -INFINITY) ? 0.f : ex2(t.c - safe_c(t.mx));
+                    p.f.stats[2 * (size_t)r] = t.mx;
+                    p.f.stats[2 * (size_t)r + 1] = t.l * f;
                 }
-                t2 = __shfl_sync(0xffffffffu, t2, 0);
-                if (t2 == g.R - 1) {
-                    __threadfence();
-                    float s = 0.f;
-                    for (int i = lane; i < g.R; i += 32) s += __ldcg(p.f.row_loss + i);
+                __stcg(p.f.row_loss + r, (fabsf(cx - gtx) * v + fabsf(cy - gty) * v + fabsf(cz - gtz) * v * hd) / 3.f);
+            }
+        }
+        // ---- one ticket per exchanger warp: the last one of the grid reduces the loss terms (index order), bumps the epoch
+        int t2 = 0;
+        if (lane == 0) {
+            __threadfence();
+            t2 = atomicAdd(p.f.done_rows, 1);
+        }
+        t2 = __shfl_sync(0xffffffffu, t2, 0);
+        if (t2 == (int)gridDim.x * NB - 1) {
+            __threadfence();
+            float s = 0.f;
+            for (int i = lane; i < g.R; i += 32) s += __ldcg(p.f.row_loss + i);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) { p.f.loss[0] = s / (float)g.R; *p.f.done_rows = 0; }
-                }
-            }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) { p.f.loss[0] = s / (float)g.R; *p.f.done_rows = 0; *p.epoch = (int)tag; }
         }
         return;
     }
@@ -177,7 +201,7 @@ __global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const Fuse
     constexpr int VPC = CHUNK_BYTES / 16;
     constexpr int U = (VPC / NC) < 1 ? 1 : ((VPC / NC) > 4 ? 4 : (VPC / NC));
     constexpr int QPV = Elem<T>::QPV;
-    const int tid = threadIdx.x - 64, wid = warp - 2;
+    const int tid = threadIdx.x - (NB + 1) * 32, wid = warp - (NB + 1);
     const bool fast = fast_ok<NC, VPC>(g);
     const uint32_t Fv = fast ? g.divFv.d : 1;
     const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NC / Fv), hf = u2f((uint32_t)g.H);
@@ -206,19 +230,19 @@ __global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const Fuse
         if (fast) a.sx = fmaf(x0f, a.l, a.sx);
         a = acc_warp_merge(a);
         if (lane == 0) {
-            partial_to_smem(pbuf[(u & 1) * NCW + wid], a);
-            mbar_arrive(part_full + (u & 1));
+            partial_to_smem(pbuf[(u % NB) * NCW + wid], a);
+            mbar_arrive(part_full + (u % NB));
         }
     };
     auto pass2 = [&](uint32_t u) {          // the same unit again (L2 hits), gradient out
         const uint32_t r = group + u * ngroups;
-        const uint32_t par = u & 1;
-        mbar_wait(rk_full + par, (u >> 1) & 1, 5);
+        const uint32_t b = u % NB;
+        mbar_wait(rk_full + b, (u / NB) & 1, 5);
         RowK rk;
-        const volatile float* c = rowk + par * 8;
+        const volatile float* c = rowk + b * 8;
         rk.c = c[0]; rk.gx = c[1]; rk.gy = c[2]; rk.gz = c[3]; rk.cx = c[4]; rk.cy = c[5]; rk.cz = c[6];
         __syncwarp();
-        if (lane == 0) mbar_arrive(rk_empty + par);
+        if (lane == 0) mbar_arrive(rk_empty + b);
         float tx[4 * QPV];
         make_tx<4 * QPV>(rk, x0f, tx);
         for (uint32_t k = k0; k < k1; ++k, ++it) {
@@ -240,9 +264,9 @@ __global__ void __launch_bounds__(NCW * 32 + 64, 1) fused_ring_kernel(const Fuse
         }
     };
 
-    if (nunits) pass1(0);
+    for (uint32_t u = 0; u < (uint32_t)DEPTH && u < nunits; ++u) pass1(u);
     for (uint32_t u = 0; u < nunits; ++u) {
-        if (u + 1 < nunits) pass1(u + 1);
+        if (u + DEPTH < nunits) pass1(u + DEPTH);
         pass2(u);
     }
 }
@@ -267,19 +291,35 @@ __global__ void scale_kernel(T* __restrict__ gh, size_t n_vec, size_t n_tail_sta
         Elem<T>::store1(gh + i, Elem<T>::load1(gh + i) * s);
 }
 
+// Pipeline depth (units between pass 1 and pass 2 of the same unit) and unit size.  DEPTH + 1 units per CTA are live
+// in L2 between their two passes; tools/l2reuse.cu puts the cliff near 148 x 512 KiB.  Measured on B=32, J=18, 64^3
+// fp32 (profiles/r01_fused_sweep.txt): 128 KiB units (S = 8) with DEPTH 2 is the best point -- smaller units trade
+// too often (each exchange costs a few loaded-L2 round trips), deeper look-ahead spills out of L2.
+// IHPR_FUSED_DEPTH / IHPR_FUSED_SPLIT override the choice for tuning experiments.
+static int fused_depth() {
+    const char* e = getenv("IHPR_FUSED_DEPTH");
+    const int d = e ? atoi(e) : 2;
+    return d < 1 ? 1 : (d > 3 ? 3 : d);
+}
+
 int fused_split(const Geometry& g, int dtype) {
     const uint64_t row_bytes = (uint64_t)g.N * (dtype == 0 ? 4 : 2);
+    if (const char* e = getenv("IHPR_FUSED_SPLIT")) {
+        int S = atoi(e);
+        while (S > 1 && (uint32_t)S > g.nch) S /= 2;
+        return S < 1 ? 1 : (S > kMaxSplit ? kMaxSplit : S);
+    }
+    const uint64_t target = 128u << 10;
     int S = 1;
-    // two units per CTA are live (pass 2 of one, pass 1 of the next): 148 * 2 * 128 KiB = 37 MiB stays in L2
-    while (row_bytes / S > (128u << 10) && S < 16 && (uint32_t)(2 * S) <= g.nch) S *= 2;
+    while (row_bytes / S > target && S < kMaxSplit && (uint32_t)(2 * S) <= g.nch) S *= 2;
     return S;
 }
 
-template <typename T>
-static cudaError_t launch_fused_t(const FusedParams& p, int num_sms, cudaStream_t s) {
-    constexpr int CB = 32768, ST = 6, NCW = 16;
-    auto kern = fused_ring_kernel<T, CB, ST, NCW>;
-    const size_t smem = (size_t)ST * CB + (2 * ST + 6) * sizeof(uint64_t) + (2 * NCW + 2) * 8 * sizeof(float);
+template <typename T, int DEPTH>
+static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_t s) {
+    constexpr int CB = 32768, ST = 6, NCW = 16, NB = DEPTH + 1;
+    auto kern = fused_ring_kernel<T, CB, ST, NCW, DEPTH>;
+    const size_t smem = (size_t)ST * CB + (2 * ST + 3 * NB) * sizeof(uint64_t) + (size_t)(NB * NCW + NB) * 8 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int S = p.S;
@@ -288,7 +328,7 @@ static cudaError_t launch_fused_t(const FusedParams& p, int num_sms, cudaStream_
     if (G > need) G = need;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
-    cfg.blockDim = dim3(NCW * 32 + 64);
+    cfg.blockDim = dim3((NCW + DEPTH + 2) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -297,6 +337,15 @@ static cudaError_t launch_fused_t(const FusedParams& p, int num_sms, cudaStream_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T>
+static cudaError_t launch_fused_t(const FusedParams& p, int num_sms, cudaStream_t s) {
+    switch (fused_depth()) {
+        case 1: return launch_fused_d<T, 1>(p, num_sms, s);
+        case 2: return launch_fused_d<T, 2>(p, num_sms, s);
+        default: return launch_fused_d<T, 3>(p, num_sms, s);
+    }
 }
 
 cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s) {
