@@ -156,6 +156,7 @@ class _IntegralL1Fused(torch.autograd.Function):
                                              hd.data_ptr(), loss.data_ptr(), coords.data_ptr(), stats.data_ptr(),
                                              grad_unit.data_ptr(), ws.data_ptr(), ws.numel(), stream))
         ctx.joint_num = J
+        ctx.dtype_code = _dtype_code(heat)
         ctx.grad_unit = grad_unit           # consumed (scaled in place) by the first backward
         ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
         ctx.mark_non_differentiable(coords)
@@ -163,22 +164,27 @@ class _IntegralL1Fused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_coords):
+        grad_heat = ctx.grad_unit
+        go = grad_loss if grad_loss.dtype == torch.float32 else grad_loss.to(torch.float32)
+        L = lib()
+        if grad_heat is not None:           # the usual case, kept short: it runs on autograd's thread between two launches
+            ctx.grad_unit = None
+            dev = grad_heat.device
+            if torch.cuda.current_device() != dev.index:
+                torch.cuda.set_device(dev)
+            check(L.ihpr_scale_grad(grad_heat.data_ptr(), ctx.dtype_code, grad_heat.numel(), go.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream))
+            return grad_heat, None, None, None
         heat, coords, stats, gt, vis, hd = ctx.saved_tensors
         J = ctx.joint_num
         B, D, H, W = _shape(heat, J)
-        go = grad_loss.to(torch.float32).contiguous()
-        L = lib()
         with torch.cuda.device(heat.device):
+            # a second backward through a retained graph: the unit gradient is gone, recompute with K2
             stream = torch.cuda.current_stream(heat.device).cuda_stream
-            grad_heat = ctx.grad_unit
-            if grad_heat is not None:
-                ctx.grad_unit = None
-                check(L.ihpr_scale_grad(grad_heat.data_ptr(), _dtype_code(heat), grad_heat.numel(), go.data_ptr(), stream))
-            else:                           # a second backward through a retained graph: recompute (K2)
-                grad_heat = torch.empty_like(heat)
-                check(L.ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
-                                             stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
-                                             go.data_ptr(), grad_heat.data_ptr(), stream))
+            grad_heat = torch.empty_like(heat)
+            check(L.ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
+                                         stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
+                                         go.data_ptr(), grad_heat.data_ptr(), stream))
         return grad_heat, None, None, None
 
 
