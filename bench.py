@@ -41,6 +41,12 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     ap.add_argument("--slices", type=int, default=8)
+    ap.add_argument("--workload", default="path", choices=["path", "train"],
+                    help="path: the soft-argmax/loss hot path (headline); train: ResNet + head + integral loss training step")
+    ap.add_argument("--resnet", type=int, default=50)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
+    ap.add_argument("--unfused-loss", action="store_true", help="train workload: K1 + K2 instead of K5")
+    ap.add_argument("--torch-loss", action="store_true", help="train workload: the reference's eager torch loss on the GPU (comparison arm)")
     return ap.parse_args()
 
 
@@ -336,10 +342,111 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+TRAIN_GFLOP_PER_SAMPLE = {50: 50.55, 152: 108.7}      # conv/deconv MACs x 2, train = 3 x forward, J=18
+
+
+def run_train(args):
+    """BASELINE.json configs[1..3]: ResNet-50 + deconv head + integral loss, synthetic 256x256, B=32 per GPU,
+    one process per GPU, NCCL gradient all-reduce (torch DDP).  Backbone/head are stock PyTorch + cuDNN (out of the
+    hot path's scope); the criterion is the sm_100a path.  One JSON line: training samples/s."""
+    import types
+    import torch
+    import torch.distributed as dist
+    import ihpr_b200
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload train needs CUDA")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True                      # main/train.py:34-37
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = args.precision != "fp32"
+    B, J = args.batch, args.joints
+    cfg = types.SimpleNamespace(resnet_type=args.resnet, depth_dim=args.depth, input_shape=(4 * args.hw, 4 * args.hw),
+                                output_shape=(args.hw, args.hw), lr=1e-3, lr_dec_epoch=[210, 280], lr_dec_factor=0.1, batch_size=B)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, J)
+    crit = None
+    if args.torch_loss:
+        from oracle.soft_argmax_ref import RefJointLocationLoss     # comparison arm only: the reference's eager loss on the GPU
+        crit = RefJointLocationLoss()
+    elif args.unfused_loss:
+        crit = ihpr_b200.JointLocationLoss(fused_backward=False)
+    tr = Trainer(net, cfg, criterion=crit, device=dev, autocast_dtype=torch.bfloat16 if args.precision == "bf16" else None,
+                 channels_last=True)
+    host = synthetic_batch(B, J, cfg, None, seed=100 + rank, pin=True)
+    devb = [t.to(dev) for t in host]
+    for _ in range(max(args.warmup, 3)):
+        tr.train_step(*devb)
+    torch.cuda.synchronize()
+    K = args.steps
+
+    def timed(from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for _ in range(K):
+            batch = [t.to(dev, non_blocking=True) for t in host] if from_host else devb
+            last = tr.train_step(*batch)
+            if from_host:
+                last = last.item()                       # device -> host read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = t.tolist()
+        return ms / K, wall / K, last
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_dev, _, _ = timed(False)
+    clocks = sampler.stop() if rank == 0 else None
+    _, wall_e2e, last = timed(True)
+    if rank == 0:
+        peaks_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf_peak = float(peaks_json.get("bf16_tflops_sustained", 1400.0))
+        gflop = TRAIN_GFLOP_PER_SAMPLE.get(args.resnet)
+        value = world * B / (ms_dev * 1e-3)
+        ach = (gflop * B / (ms_dev * 1e-3) / 1e3) if gflop and J == 18 else None
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        print(json.dumps({
+            "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "ResNet-%d + deconv head + integral L1 loss training step (Adam), synthetic %dx%d, B=%d per GPU, J=%d, D=%d, "
+                                   "DDP NCCL all-reduce" % (args.resnet, 4 * args.hw, 4 * args.hw, B, J, args.depth),
+                       "criterion": "torch eager (reference ops)" if args.torch_loss else ("ihpr_b200 K1+K2" if args.unfused_loss else "ihpr_b200 K5"),
+                       "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark"},
+            "clocks": clocks,
+            "e2e": {"value": world * B / wall_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": wall_e2e * 1e3,
+                    "last_loss": last},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": (ach / tf_peak) if ach else None,
+                         "note": "whole-step model FLOPs (SURVEY 8d) / step time vs sustained bf16 GEMM peak; the convolutions are cuDNN's, not this repo's"},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_b200(args)
 

@@ -1,0 +1,69 @@
+"""Model-side mirror of /root/reference/main/model.py for the end-to-end harness.
+
+Same module tree and parameter names as the reference (`backbone.*`, `head.deconv_layers.{0,1,3,4,6,7}.*`,
+`head.final_layer.{weight,bias}`) so checkpoints written by the reference (with their DataParallel `module.` prefix,
+see trainer.load_reference_checkpoint) load unchanged.  `ResPoseNet.forward(input_img, target=None)` is the superset
+contract `north_star` asks for: without a target it returns the heat-map exactly like the reference
+(model.py:99-103); with `target = {'coord', 'vis', 'have_depth'}` it returns the integral L1 loss computed by the
+sm_100a path (what main/train.py:64-67 does in two calls).
+"""
+import torch.nn as nn
+
+from .nets.loss import JointLocationLoss, soft_argmax
+from .nets.resnet import ResNetBackbone
+
+
+class HeadNet(nn.Module):
+    """3 x (ConvTranspose2d k4 s2 p1 -> BatchNorm -> ReLU) then the 1x1 conv to J*depth_dim channels (model.py:5-44)."""
+
+    def __init__(self, joint_num, depth_dim=64, inplanes=2048, outplanes=256):
+        super().__init__()
+        layers = []
+        for _ in range(3):
+            layers += [nn.ConvTranspose2d(inplanes, outplanes, kernel_size=4, stride=2, padding=1, output_padding=0, bias=False),
+                       nn.BatchNorm2d(outplanes), nn.ReLU(inplace=True)]
+            inplanes = outplanes
+        self.deconv_layers = nn.Sequential(*layers)
+        self.final_layer = nn.Conv2d(inplanes, joint_num * depth_dim, kernel_size=1, stride=1, padding=0)
+
+    def forward(self, x):
+        return self.final_layer(self.deconv_layers(x))
+
+    def init_weights(self):                            # model.py:46-56
+        for m in self.modules():
+            if isinstance(m, (nn.ConvTranspose2d, nn.Conv2d)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+class ResPoseNet(nn.Module):
+    def __init__(self, backbone, head, joint_num=None):
+        super().__init__()
+        self.backbone = backbone
+        self.head = head
+        self.joint_num = joint_num
+        self.criterion = JointLocationLoss()
+
+    def forward(self, input_img, target=None):
+        heatmap = self.head(self.backbone(input_img))
+        if target is None:
+            return heatmap                             # reference contract, model.py:99-103
+        return self.criterion(heatmap, target["coord"], target["vis"], target["have_depth"])
+
+    def predict(self, input_img):
+        """Inference: (B, J, 3) voxel coordinates, i.e. main/test.py:62-65 without the full-heat-map gather."""
+        return soft_argmax(self.forward(input_img), self.joint_num)
+
+
+def get_pose_net(cfg, is_train, joint_num):
+    """model.py:105-114.  `cfg` needs `resnet_type` and `depth_dim` (main/config.py:24,28)."""
+    backbone = ResNetBackbone(cfg.resnet_type)
+    head = HeadNet(joint_num, depth_dim=cfg.depth_dim, inplanes=backbone.out_channels)
+    if is_train:
+        backbone.init_weights()
+        head.init_weights()
+    return ResPoseNet(backbone, head, joint_num)

@@ -83,5 +83,30 @@ def main():
               f"{os.path.getsize(path)/1024:.0f} KiB")
 
 
+def dump_reference_state_keys():
+    """state_dict keys + shapes of the reference's own get_pose_net (main/model.py:105-114) for ResNet-50 / J=18,
+    as a fixture for the checkpoint-compatibility test of ihpr_b200.model (the reference's resnet.py imports
+    `model_zoo, model_urls` which torchvision >= 0.13 no longer exports: two placeholder attributes let it import)."""
+    import torchvision.models.resnet as tvr
+    if not hasattr(tvr, "model_zoo"):
+        tvr.model_zoo, tvr.model_urls = None, {}
+    ref = Reference()
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ref.tmp, "ref", "main"))
+    try:
+        import model as ref_model
+    finally:
+        os.chdir(cwd)
+    ref.cfg.resnet_type, ref.cfg.depth_dim = 50, 64
+    net = ref_model.get_pose_net(ref.cfg, False, 18)
+    path = os.path.join(GOLDEN_DIR, "reference_state_keys_r50_j18.txt")
+    with open(path, "w") as f:
+        for k, v in net.state_dict().items():
+            f.write("module.%s %s\n" % (k, "x".join(str(d) for d in v.shape)))
+    print("wrote", path)
+
+
 if __name__ == "__main__":
-    main()
+    if "--keys" not in sys.argv:
+        main()
+    dump_reference_state_keys()

@@ -305,3 +305,32 @@ def test_host_buffer_entry_point(dev):
     assert abs(loss.item() - l64) <= TOL * max(1.0, abs(l64))
     assert coord_err(coords.numpy(), c64) <= TOL and grad_err(grad.numpy(), g64) <= TOL
     assert ihpr_b200.last_launch_count() == 2 * 3 + 1
+
+
+def test_model_forward_input_target_contract(dev):
+    """ResPoseNet.forward(input, target): heat-map without a target (main/model.py:99-103), integral loss with one
+    (main/train.py:64-67 in one call); gradients reach the parameters and match the oracle criterion's."""
+    import types
+    import ihpr_b200
+    from ihpr_b200.model import get_pose_net
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=8, input_shape=(64, 64), output_shape=(16, 16))
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 4).to(dev)
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.05)       # make the heat-maps non-trivial
+    x = torch.randn(3, 3, 64, 64, device=dev)
+    tgt = {"coord": torch.rand(3, 4, 3, device=dev) * torch.tensor([16, 16, 8], device=dev), "vis": torch.ones(3, 4, 1, device=dev),
+           "have_depth": torch.ones(3, 1, device=dev)}
+    heat = net(x)
+    assert heat.shape == (3, 32, 16, 16)
+    loss = net(x, tgt)
+    loss.backward()
+    g_ours = net.head.final_layer.weight.grad.clone()
+    net.zero_grad()
+    net.criterion = RefJointLocationLoss()
+    loss_ref = net(x, tgt)
+    loss_ref.backward()
+    g_ref = net.head.final_layer.weight.grad
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
+    assert (g_ours - g_ref).abs().max().item() <= 1e-3 * g_ref.abs().max().item()
+    assert net.predict(x).shape == (3, 4, 3)

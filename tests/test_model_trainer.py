@@ -1,0 +1,105 @@
+"""CPU: the model mirror keeps the reference's parameter names / shapes (checkpoint compatibility), and the
+one-process-per-GPU trainer logic (batch sharding, mean-of-rank-means, gradient averaging) matches a single
+process -- exercised with world_size 2 over gloo.  The CUDA criterion cannot run here, so the trainer is given the
+oracle's torch restatement of JointLocationLoss as its criterion (tests may use the oracle; the product never does)."""
+import os
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN_DIR, ROOT
+
+
+def tiny_cfg():
+    return types.SimpleNamespace(resnet_type=18, depth_dim=4, input_shape=(32, 32), output_shape=(8, 8), lr=1e-3,
+                                 lr_dec_epoch=[2, 3], lr_dec_factor=0.1, batch_size=4)
+
+
+def test_state_dict_matches_reference_keys(built_lib):
+    from ihpr_b200.model import get_pose_net
+    cfg = types.SimpleNamespace(resnet_type=50, depth_dim=64)
+    net = get_pose_net(cfg, False, 18)
+    ours = {"module." + k: "x".join(str(d) for d in v.shape) for k, v in net.state_dict().items()}
+    ref = {}
+    for line in open(os.path.join(GOLDEN_DIR, "reference_state_keys_r50_j18.txt")):
+        parts = line.rstrip("\n").split(" ")
+        ref[parts[0]] = parts[1] if len(parts) > 1 else ""
+    assert ours == ref          # names, order-independent, and shapes: the reference's checkpoints load unchanged
+
+
+def test_forward_contract_and_checkpoint_roundtrip(built_lib, tmp_path):
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, synthetic_batch
+    cfg = tiny_cfg()
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3)
+    tr = Trainer(net, cfg, criterion=RefJointLocationLoss())
+    img, coord, vis, hd = synthetic_batch(4, 3, cfg, None, seed=1)
+    heat = net(img)                                       # forward(x) -> heat-map, main/model.py:99-103
+    assert heat.shape == (4, 3 * cfg.depth_dim, 8, 8)
+    l0 = tr.train_step(img, coord, vis, hd)
+    assert l0.dim() == 0 and torch.isfinite(l0)
+    tr.save(str(tmp_path))
+    ck = torch.load(os.path.join(str(tmp_path), "snapshot_0.pth.tar"))
+    assert set(ck) == {"epoch", "network", "optimizer", "scheduler"} and all(k.startswith("module.") for k in ck["network"])
+    net2 = get_pose_net(cfg, True, 3)
+    tr2 = Trainer(net2, cfg, criterion=RefJointLocationLoss())
+    tr2.load(os.path.join(str(tmp_path), "snapshot_0.pth.tar"))
+    assert tr2.epoch == 1
+    for a, b in zip(net.state_dict().values(), net2.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def _ddp_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, global_mean_of_rank_means, shard_range, synthetic_batch
+    cfg = tiny_cfg()
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3)
+    for m in net.modules():                               # batch statistics differ per shard: freeze BN for the comparison
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 0.0
+            m.eval()
+    tr = Trainer(net, cfg, criterion=RefJointLocationLoss())
+    tr.model.train = lambda *a, **k: tr.model          # keep BN in eval mode inside train_step
+    img, coord, vis, hd = synthetic_batch(4, 3, cfg, None, seed=1)
+    lo, hi = shard_range(4, rank, world)
+    loss = tr.train_step(img[lo:hi], coord[lo:hi], vis[lo:hi], hd[lo:hi])
+    g = global_mean_of_rank_means(loss)
+    if rank == 0:
+        torch.save({"loss": g, "w": tr.raw_model.head.final_layer.weight.detach().clone()}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_step_equals_single_process(built_lib, tmp_path):
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, shard_range, synthetic_batch
+    assert shard_range(5, 0, 2) == (0, 2) and shard_range(5, 1, 2) == (2, 5)
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    cfg = tiny_cfg()
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 0.0
+            m.eval()
+    tr = Trainer(net, cfg, criterion=RefJointLocationLoss())
+    tr.model.train = lambda *a, **k: tr.model
+    img, coord, vis, hd = synthetic_batch(4, 3, cfg, None, seed=1)
+    loss = tr.train_step(img, coord, vis, hd)
+    # mean of the two rank means == global mean (equal shards, balanced_parallel.py:127); averaged gradients == global gradient
+    assert abs(got["loss"].item() - loss.item()) <= 1e-6
+    assert torch.allclose(got["w"], net.head.final_layer.weight, atol=1e-6)
