@@ -115,7 +115,7 @@ def make_inputs_torch(B, J, D, H, W, device, dtype, seed):
     return heat, gt, vis, hd
 
 
-def cpu_reference_leg(B, J, D, H, W, min_seconds, warmup=2, max_iters=50):
+def cpu_reference_leg(B, J, D, H, W, min_seconds, warmup=2, max_iters=100000):
     """The reference's CPU path (oracle/soft_argmax_ref.py: the same ATen calls as loss.py:13-52 + autograd),
     all host threads, on a bounded sample of the workload.  Returns (volumes/s, cores, iters, seconds)."""
     import torch
@@ -139,6 +139,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     B, J, D, W = args.batch, args.joints, args.depth, args.hw
     sample_B = min(B, 8)
     from oracle.soft_argmax_ref import ref_fwd_bwd
@@ -319,7 +320,8 @@ def run_b200(args):
              "step_GBps_of_3V_incl_launch_gaps": 3 * V / (ms_per_step * 1e-3) / 1e9}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
         sB = 4
         v, cores, n, dt = cpu_reference_leg(sB, J, D, H, W, min_seconds=10.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

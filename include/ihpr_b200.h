@@ -99,6 +99,15 @@ int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, i
  * ihpr_integral_l1_fwd_bwd into autograd's answer for an arbitrary upstream gradient.  n = B*J*D*H*W elements. */
 int ihpr_scale_grad(void *grad_heat, int dtype, size_t n, const float *grad_out, void *stream);
 
+/* HeadNet.final_layer (1x1 conv with bias, main/model.py:14-20,42) fused with soft_argmax (loss.py:13-34), forward:
+ * coords of the heat-map  W x + b  without ever writing the heat-map (tcgen05 / TMEM GEMM with a soft-argmax epilogue).
+ * x_nhwc: (B, H, W, K) bf16, i.e. the (B, K, H, W) activations in channels_last memory format; weight: (J*D, K) bf16
+ * row-major (= Conv2d weight (J*D, K, 1, 1)); bias: (J*D) fp32.  Needs K % 64 == 0, K <= 256, D in {32, 64, 128},
+ * W % 32 == 0, H*W % 256 == 0.  Replaces main/test.py:62-65 (model forward tail + soft_argmax) under no_grad. */
+int ihpr_head_softargmax_fwd(const void *x_nhwc, const void *weight, const float *bias,
+                             int B, int K, int J, int D, int H, int W,
+                             float *coords, float *stats, void *stream);
+
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in
  * `slices` batch slices pipelined over internal streams, runs forward + backward and copies

@@ -272,6 +272,25 @@ int ihpr_scale_grad(void* grad_heat, int dtype, size_t n, const float* grad_out,
     return IHPR_OK;
 }
 
+int ihpr_head_softargmax_fwd(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
+                             float* stats, void* stream) {
+    g_launches = 0;
+    if (!x_nhwc || !weight || !bias || !coords) return fail(IHPR_EINVAL, "null argument");
+    if (B <= 0 || J <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if (K <= 0 || K % 64 != 0 || K > 256) return fail(IHPR_EINVAL, "fused head needs K a multiple of 64, at most 256 (got %d)", K);
+    if (D != 32 && D != 64 && D != 128) return fail(IHPR_EINVAL, "fused head needs depth_dim 32, 64 or 128 (got %d)", D);
+    if (H <= 0 || W <= 0 || (H * W) % 256 != 0 || W % 32 != 0) return fail(IHPR_EINVAL, "fused head needs W %% 32 == 0 and H*W %% 256 == 0 (got %dx%d)", H, W);
+    if (((uintptr_t)x_nhwc | (uintptr_t)weight) & 15) return fail(IHPR_EINVAL, "x / weight must be 16-byte aligned");
+    int num_sms = 0;
+    int rc = check_device(x_nhwc, &num_sms);
+    if (rc) return rc;
+    const char* err = ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, num_sms, static_cast<cudaStream_t>(stream));
+    if (err) return fail(IHPR_ECUDA, "%s", err);
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
                                   const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
                                   int device, int slices) {

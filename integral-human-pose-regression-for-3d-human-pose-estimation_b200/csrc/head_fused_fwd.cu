@@ -1,0 +1,307 @@
+// head_fused_fwd.cu -- K3: HeadNet.final_layer (1x1 conv, /root/reference/main/model.py:14-20,42) fused with the
+// 3-D soft-argmax (/root/reference/common/nets/loss.py:13-34): the J*D x H x W heat-map never exists in HBM.
+//
+// Per sample b the 1x1 conv is the GEMM  Hm[c, n] = sum_k Wt[c, k] * X[b, n, k] + bias[c]
+//   c = j*D + d  (M = J*D output channels),  n = y*W + x (N = H*W pixels),  k < K = 256 input channels,
+// on the 5th-generation tensor cores:  tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 (bf16 in, fp32 accumulate),
+// both operands K-major in shared memory (X is taken in NHWC / channels_last, the layout the cuDNN deconv emits), staged
+// by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B), accumulator in TMEM (2 stages x 256 columns, so the MMA of the next
+// pixel tile overlaps the epilogue of this one).  TMEM lane = output channel = (joint, z); TMEM column = pixel (y, x).
+//
+// Work item = (sample b, 128-channel tile).  One persistent CTA per SM walks items b*MT + mt, so the CTAs that share a
+// sample run together and its X tiles come out of L2.  Per item the Wt tile (128 x K bf16, 64 KiB) is loaded once and
+// the 16 pixel tiles of X[b] stream through a 4-stage ring of 256 x 64 k-blocks.
+//
+// Epilogue (8 warps; warp%4 selects the TMEM lane quarter, warp/4 the column half): tcgen05.ld 32 columns at a time,
+// online softmax over pixels per lane with the same lazy re-base as K1, sum p, sum p*x, sum p*y per lane (z is the
+// lane's constant); after the last pixel tile the D lanes x 2 halves of a joint are merged and coords / stats written.
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..11 = epilogue.
+#include <cuda.h>
+
+#include "ihpr_device.cuh"
+
+namespace ihpr {
+
+namespace k3 {
+constexpr int BM = 128;             // channels per tile = UMMA M
+constexpr int BN = 256;             // pixels per tile   = UMMA N
+constexpr int BK = 64;              // k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int STAGES = 4;           // ring of X k-blocks
+constexpr int MAXKB = 4;            // K <= 256
+constexpr int A_KB_BYTES = BM * BK * 2;     // 16 KiB
+constexpr int B_KB_BYTES = BN * BK * 2;     // 32 KiB
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (4 + EPI_WARPS);
+constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 fp32 columns
+
+struct Params {
+    int B, K, J, D, H, W;
+    int MT;                 // channel tiles = ceil(J*D / 128)
+    int NT;                 // pixel tiles = H*W / 256
+    int KB;                 // k-blocks = K / 64
+    const float* bias;      // (J*D)
+    float* coords;          // (B, J, 3)
+    float* stats;           // (B, J, 2) or null
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start >> 4, LBO = 1 (unused),
+// SBO = 1024 B (8 rows x 128 B), version = 1 (Blackwell), layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                     // [KB][128 x 64] bf16
+    uint8_t* sB = smem + MAXKB * A_KB_BYTES;                // [STAGES][256 x 64] bf16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_KB_BYTES);
+    uint64_t* b_full = bars;                // [STAGES] TMA -> MMA
+    uint64_t* b_empty = bars + STAGES;      // [STAGES] MMA -> TMA (tcgen05.commit)
+    uint64_t* a_full = bars + 2 * STAGES;   // [1]
+    uint64_t* a_empty = a_full + 1;         // [1]      MMA -> TMA: the item's last MMA has read Wt
+    uint64_t* t_full = a_empty + 1;         // [2]      MMA -> epilogue: accumulator stage complete
+    uint64_t* t_empty = t_full + 2;         // [2]      epilogue -> MMA: accumulator stage drained (EPI_WARPS arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_WARPS][8]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.B * p.MT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {        // TMEM allocation: one warp, result through shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0, n_item = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                const int b = item / p.MT, mt = item - b * p.MT;
+                mbar_wait(a_empty, (n_item & 1) ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_KB_BYTES));
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &map_w, kb * BK, mt * BM, a_full);
+                for (int nt = 0; nt < p.NT; ++nt)
+                    for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(b_empty + s, ph ^ 1);
+                        mbar_expect_tx(b_full + s, (uint32_t)B_KB_BYTES);
+                        tma_load_2d(sB + s * B_KB_BYTES, &map_x, kb * BK, b * p.NT * BN + nt * BN, b_full + s);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, n_item = 0, acc_it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                mbar_wait(a_full, n_item & 1);
+                for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(t_empty + as, aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BN;
+                    for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(b_full + s, ph);
+                        tc_fence_after();
+                        const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * B_KB_BYTES));
+#pragma unroll
+                        for (int k16 = 0; k16 < BK / 16; ++k16)      // +32 B per K=16 step inside the 128 B swizzle row: +2 in the (>>4) address field
+                            umma(tmem_d, ad + 2 * k16, bd + 2 * k16, (uint32_t)((kb | k16) != 0));
+                        tc_commit(b_empty + s);          // frees the X stage when these MMAs have read it
+                    }
+                    tc_commit(t_full + as);              // accumulator stage complete
+                }
+                tc_commit(a_empty);                      // Wt tile may be overwritten
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int e = warp - 4;
+        const int qd = warp & 3;                 // TMEM lane quarter this warp may read
+        const int ch = e >> 2;                   // column half
+        const int lane_c = qd * 32 + lane;       // channel within the tile = TMEM lane
+        const FastDiv divW = make_fastdiv((uint32_t)p.W);
+        uint32_t acc_it = 0, n_item = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+            const int b = item / p.MT, mt = item - b * p.MT;
+            const int c = mt * BM + lane_c;                      // output channel
+            const bool valid = c < p.J * p.D;
+            const float bias_f = valid ? __ldg(p.bias + c) : 0.f;
+            const float bias2 = bias_f * kLog2e;
+            const float zf = (float)(c % p.D);
+            // weights are 2^(acc*log2e + bias2 - cref); (m, c) of Acc hold the reference point of (acc + bias)
+            Acc a;
+            a.reset();
+            for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
+                const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(t_full + as, aph);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * (BN / 2);
+#pragma unroll 1
+                for (int j = 0; j < BN / 2 / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tbase + j * 32, v);
+                    const uint32_t pix = (uint32_t)(nt * BN + ch * (BN / 2) + j * 32);     // first pixel of this 32-column group
+                    const uint32_t y = fdiv(pix, divW);
+                    const float yf = u2f(y), x0f = u2f(pix - y * divW.d);
+                    float cmax = v[0];
+#pragma unroll
+                    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
+                    // reference point in "h" units: h = acc + bias
+                    const float hmax = cmax + bias_f;
+                    a.mx = fmaxf(a.mx, hmax);
+                    if (hmax > a.lim) acc_raise(a, hmax);
+                    const float k0 = bias2 - a.c;
+                    float s = 0.f, w = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float pw = ex2(fmaf(v[i], kLog2e, k0));
+                        s += pw;
+                        w = fmaf(pw, (float)i, w);
+                    }
+                    a.l += s;
+                    a.sx += fmaf(x0f, s, w);
+                    a.sy = fmaf(yf, s, a.sy);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + as);
+            }
+            // ---- merge the lanes (z) and the two column halves of each joint, write coords / stats
+            if (!valid) a.reset();
+            a.sz = zf * a.l;
+            a = acc_warp_merge(a);              // 32 lanes of one warp always belong to one joint (D % 32 == 0)
+            float(*rb)[8] = red + (n_item & 1) * EPI_WARPS;
+            if (lane == 0) partial_to_smem(rb[e], a);
+            named_bar_sync(1, EPI_WARPS * 32);
+            const int jpt = BM / p.D;           // joints per channel tile
+            if (e == 0 && lane < jpt) {
+                const int jt = lane;
+                Acc t;
+                t.reset();
+                const int q0 = jt * p.D / 32, q1 = (jt + 1) * p.D / 32;       // lane quarters of this joint
+                for (int qq = q0; qq < q1; ++qq)
+                    for (int hh = 0; hh < 2; ++hh) t = acc_merge(t, partial_from_smem(rb[hh * 4 + qq]));
+                const int joint = mt * jpt + jt;
+                if (joint < p.J) {
+                    const size_t r = (size_t)b * p.J + joint;
+                    const float inv = 1.0f / t.l;
+                    p.coords[3 * r + 0] = t.sx * inv;
+                    p.coords[3 * r + 1] = t.sy * inv;
+                    p.coords[3 * r + 2] = t.sz * inv;
+                    if (p.stats) {
+                        const float f = (t.m == -INFINITY) ? 0.f : ex2(t.c - safe_c(t.mx));
+                        p.stats[2 * r] = t.mx;
+                        p.stats[2 * r + 1] = t.l * f;
+                    }
+                }
+            }
+            // red[] is double-buffered by item parity; the barrier of the NEXT item orders its reuse
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+}  // namespace k3
+
+// ---- host side --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][K] (K contiguous), box [box_rows][64], SWIZZLE_128B
+static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)k3::BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
+                              float* stats, int num_sms, cudaStream_t s) {
+    k3::Params p;
+    p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
+    p.MT = (J * D + k3::BM - 1) / k3::BM;
+    p.NT = H * W / k3::BN;
+    p.KB = K / k3::BK;
+    p.bias = bias; p.coords = coords; p.stats = stats;
+    CUtensorMap map_w, map_x;
+    if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
+    if (!make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
+    const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + k3::STAGES * k3::B_KB_BYTES + 32 * sizeof(uint64_t) + 2 * k3::EPI_WARPS * 8 * sizeof(float);
+    if (cudaFuncSetAttribute(k3::head_softargmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return "cudaFuncSetAttribute failed";
+    int grid = B * p.MT;
+    if (grid > num_sms) grid = num_sms;
+    k3::head_softargmax_kernel<<<grid, k3::THREADS, smem, s>>>(map_w, map_x, p);
+    return nullptr;
+}
+
+}  // namespace ihpr

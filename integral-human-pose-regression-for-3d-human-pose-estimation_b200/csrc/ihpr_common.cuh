@@ -22,7 +22,7 @@ constexpr int kMinChunkElems = 2048;    // every kernel config streams chunks of
 struct FastDiv {
     uint32_t d, mul, shr;
 };
-inline FastDiv make_fastdiv(uint32_t d) {
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
     FastDiv f;
     f.d = d;
     uint32_t s = 0;
@@ -316,5 +316,7 @@ Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok
 int fused_split(const Geometry& g, int dtype);
 cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s);
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
+const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
+                              float* stats, int num_sms, cudaStream_t s);
 
 }  // namespace ihpr

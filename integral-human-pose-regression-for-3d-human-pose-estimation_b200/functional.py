@@ -266,6 +266,33 @@ def integral_l1_fwd_bwd_host(heat, gt_coord, gt_vis, gt_have_depth, grad_out=1.0
     return loss, coords, grad
 
 
+def fused_head_soft_argmax(x, weight, bias, joint_num, return_stats=False):
+    """coords of soft_argmax(conv1x1(x, weight, bias)) in ONE launch (K3: tcgen05 GEMM + soft-argmax epilogue); the
+    (B, J*D, H, W) heat-map is never written.  Forward only -- the inference tail of main/test.py:62-65.
+    x: (B, K, H, W) cuda tensor (made bf16 / channels_last if it is not), weight: (J*D, K[, 1, 1]), bias: (J*D)."""
+    _require_cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be (B, K, H, W), got %s" % (tuple(x.shape),))
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise IhprError("fused_head_soft_argmax is forward-only (use it under torch.no_grad(); training uses conv + K5)")
+    B, K, H, W = x.shape
+    M = weight.shape[0]
+    if joint_num <= 0 or M % joint_num != 0:
+        raise ValueError("%d output channels are not a multiple of joint_num %d" % (M, joint_num))
+    D = M // joint_num
+    xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)      # physical (B, H, W, K)
+    wb = weight.detach().reshape(M, K).to(torch.bfloat16).contiguous()
+    bf = (bias.detach() if bias is not None else torch.zeros(M, device=x.device)).to(torch.float32).contiguous()
+    dev = x.device
+    coords = torch.empty((B, joint_num, 3), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, joint_num, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(lib().ihpr_head_softargmax_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, joint_num, D, H, W,
+                                             coords.data_ptr(), stats.data_ptr(), stream))
+    return (coords, stats) if return_stats else coords
+
+
 def last_launch_count():
     return lib().ihpr_last_launch_count()
 
