@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--resnet", type=int, default=50)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--unfused-loss", action="store_true", help="train workload: K1 + K2 instead of K5")
+    ap.add_argument("--fused-head", action="store_true", help="train workload: final_layer + loss as K3/K4 (heat-map never stored)")
     ap.add_argument("--torch-loss", action="store_true", help="train workload: the reference's eager torch loss on the GPU (comparison arm)")
     return ap.parse_args()
 
@@ -373,7 +374,7 @@ def run_train(args):
     cfg = types.SimpleNamespace(resnet_type=args.resnet, depth_dim=args.depth, input_shape=(4 * args.hw, 4 * args.hw),
                                 output_shape=(args.hw, args.hw), lr=1e-3, lr_dec_epoch=[210, 280], lr_dec_factor=0.1, batch_size=B)
     torch.manual_seed(0)
-    net = get_pose_net(cfg, True, J)
+    net = get_pose_net(cfg, True, J, fused_head=args.fused_head)
     crit = None
     if args.torch_loss:
         from oracle.soft_argmax_ref import RefJointLocationLoss     # comparison arm only: the reference's eager loss on the GPU
@@ -431,7 +432,8 @@ def run_train(args):
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "ResNet-%d + deconv head + integral L1 loss training step (Adam), synthetic %dx%d, B=%d per GPU, J=%d, D=%d, "
                                    "DDP NCCL all-reduce" % (args.resnet, 4 * args.hw, 4 * args.hw, B, J, args.depth),
-                       "criterion": "torch eager (reference ops)" if args.torch_loss else ("ihpr_b200 K1+K2" if args.unfused_loss else "ihpr_b200 K5"),
+                       "criterion": "torch eager (reference ops)" if args.torch_loss else ("ihpr_b200 K1+K2" if args.unfused_loss else
+                                     ("ihpr_b200 K3+K4 fused with final_layer" if args.fused_head else "ihpr_b200 K5")),
                        "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark"},
             "clocks": clocks,
             "e2e": {"value": world * B / wall_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": wall_e2e * 1e3,

@@ -17,6 +17,11 @@
 // lane's constant); after the last pixel tile the D lanes x 2 halves of a joint are merged and coords / stats written.
 //
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..11 = epilogue.
+//
+// K4 (template BWD = true) is the same GEMM with another epilogue: the heat-map tile is recomputed in TMEM, turned into
+// d loss / d heat = p * sum_c g_c (c(i) - coord_c) with the (m, l, coords) K3 saved, and written as bf16 in the heat-map's
+// own (B, J*D, H, W) layout -- so training never writes or reads the heat-map, only its gradient; dW / dX / dbias are then
+// plain library GEMMs on that gradient (host side, functional.py).
 #include <cuda.h>
 
 #include "ihpr_device.cuh"
@@ -41,8 +46,15 @@ struct Params {
     int NT;                 // pixel tiles = H*W / 256
     int KB;                 // k-blocks = K / 64
     const float* bias;      // (J*D)
-    float* coords;          // (B, J, 3)
-    float* stats;           // (B, J, 2) or null
+    float* coords;          // (B, J, 3)   forward: out; backward: in
+    float* stats;           // (B, J, 2)   forward: out (or null); backward: in
+    // backward (K4) only
+    const float* gt;        // (B, J, 3)
+    const float* vis;       // (B, J)
+    const float* have_depth;// (B)
+    const float* grad_out;  // device scalar
+    float loss_scale;       // 1 / (3 * B * J)
+    __nv_bfloat16* grad_heat;   // (B, J*D, H*W) bf16 out: d loss / d heat-map, the heat-map itself is only ever a TMEM tile
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -85,6 +97,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <bool BWD>
 __global__ void __launch_bounds__(THREADS, 1)
 head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -179,6 +192,49 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
             const float bias_f = valid ? __ldg(p.bias + c) : 0.f;
             const float bias2 = bias_f * kLog2e;
             const float zf = (float)(c % p.D);
+            if constexpr (BWD) {
+                // K4: d loss / d heat = p * sum_c g_c (c(i) - coord_c), p recomputed from the TMEM tile + stats (m, l)
+                const int joint = min(c / p.D, p.J - 1);
+                const size_t r = (size_t)b * p.J + joint;
+                const float m = __ldg(p.stats + 2 * r), il = 1.0f / __ldg(p.stats + 2 * r + 1);
+                const float cx = __ldg(p.coords + 3 * r), cy = __ldg(p.coords + 3 * r + 1), cz = __ldg(p.coords + 3 * r + 2);
+                const float sc = __ldg(p.grad_out) * __ldg(p.vis + r) * p.loss_scale * il;
+                const float gx = sc * sgn(cx - __ldg(p.gt + 3 * r)), gy = sc * sgn(cy - __ldg(p.gt + 3 * r + 1));
+                const float gz = sc * sgn(cz - __ldg(p.gt + 3 * r + 2)) * __ldg(p.have_depth + b);
+                const float k0 = bias2 - safe_c(m);
+                const float tz = gz * (zf - cz);
+                __nv_bfloat16* orow = p.grad_heat + ((size_t)b * p.J * p.D + c) * ((size_t)p.H * p.W);
+                for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
+                    const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+                    mbar_wait(t_full + as, aph);
+                    tc_fence_after();
+                    const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * (BN / 2);
+#pragma unroll 1
+                    for (int j = 0; j < BN / 2 / 32; ++j) {
+                        float v[32];
+                        tmem_ld32(tbase + j * 32, v);
+                        const uint32_t pix = (uint32_t)(nt * BN + ch * (BN / 2) + j * 32);
+                        const uint32_t y = fdiv(pix, divW);
+                        const float base = fmaf(gy, u2f(y) - cy, fmaf(gx, u2f(pix - y * divW.d) - cx, tz));
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float d0 = ex2(fmaf(v[2 * i], kLog2e, k0)) * fmaf((float)(2 * i), gx, base);
+                            const float d1 = ex2(fmaf(v[2 * i + 1], kLog2e, k0)) * fmaf((float)(2 * i + 1), gx, base);
+                            o[i] = Elem<__nv_bfloat16>::pk(d0, d1);
+                        }
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(orow + pix);       // 32 pixels = 64 contiguous bytes of this channel row
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) st_stream16(dst + i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + as);
+                }
+                continue;
+            }
             // weights are 2^(acc*log2e + bias2 - cref); (m, c) of Acc hold the reference point of (acc + bias)
             Acc a;
             a.reset();
@@ -285,22 +341,27 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 }
 
 const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
-                              float* stats, int num_sms, cudaStream_t s) {
+                              float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
+                              int num_sms, cudaStream_t s) {
     k3::Params p;
     p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
     p.MT = (J * D + k3::BM - 1) / k3::BM;
     p.NT = H * W / k3::BN;
     p.KB = K / k3::BK;
     p.bias = bias; p.coords = coords; p.stats = stats;
+    p.gt = gt; p.vis = vis; p.have_depth = have_depth; p.grad_out = grad_out;
+    p.loss_scale = 1.0f / (3.0f * (float)B * (float)J);
+    p.grad_heat = static_cast<__nv_bfloat16*>(grad_heat);
+    const bool bwd = grad_heat != nullptr;
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
     if (!make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
     const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + k3::STAGES * k3::B_KB_BYTES + 32 * sizeof(uint64_t) + 2 * k3::EPI_WARPS * 8 * sizeof(float);
-    if (cudaFuncSetAttribute(k3::head_softargmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return "cudaFuncSetAttribute failed";
+    auto kern = bwd ? k3::head_softargmax_kernel<true> : k3::head_softargmax_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed";
     int grid = B * p.MT;
     if (grid > num_sms) grid = num_sms;
-    k3::head_softargmax_kernel<<<grid, k3::THREADS, smem, s>>>(map_w, map_x, p);
+    kern<<<grid, k3::THREADS, smem, s>>>(map_w, map_x, p);
     return nullptr;
 }
 

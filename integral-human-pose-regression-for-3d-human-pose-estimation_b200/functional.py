@@ -293,6 +293,70 @@ def fused_head_soft_argmax(x, weight, bias, joint_num, return_stats=False):
     return (coords, stats) if return_stats else coords
 
 
+class _FusedHeadIntegralL1(torch.autograd.Function):
+    """final_layer (1x1 conv) + soft-argmax + L1 loss with the heat-map living only in TMEM (K3 forward, K4 backward).
+    Saved for backward: the bf16 activations / weight and 5 floats per joint -- no heat-map, no softmax."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gt, vis, hd):
+        B, K, H, W = x.shape
+        M, J = weight.shape[0], gt.shape[1]
+        xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wb = weight.detach().reshape(M, K).to(torch.bfloat16).contiguous()
+        bf = bias.detach().to(torch.float32).contiguous()
+        dev = x.device
+        coords = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+        stats = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            check(lib().ihpr_head_softargmax_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
+                                                 coords.data_ptr(), stats.data_ptr(), stream))
+        # loss.py:49-52 on the (B, J, 3) coordinates: a handful of tiny ops
+        d = (coords - gt).abs() * vis.view(B, J, 1)
+        loss = ((d[..., 0] + d[..., 1] + d[..., 2] * hd.view(B, 1)) / 3.0).mean()
+        ctx.save_for_backward(xb, wb, bf, coords, stats, gt, vis, hd)
+        ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape))
+        ctx.mark_non_differentiable(coords)
+        return loss, coords
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_coords):
+        xb, wb, bf, coords, stats, gt, vis, hd = ctx.saved_tensors
+        x_dtype, w_dtype, b_dtype, w_shape = ctx.meta
+        B, K, H, W = xb.shape
+        M, J = wb.shape[0], gt.shape[1]
+        N = H * W
+        go = grad_loss.to(torch.float32).contiguous()
+        dev = xb.device
+        dheat = torch.empty((B, M, N), dtype=torch.bfloat16, device=dev)        # d loss / d heat-map, (B, J*D, H, W) layout
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            check(lib().ihpr_head_integral_l1_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
+                                                  coords.data_ptr(), stats.data_ptr(), gt.data_ptr(), vis.data_ptr(),
+                                                  hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), stream))
+        # conv backward = plain library GEMMs on the gradient (no layout changes: x is NHWC, dheat is (B, M, N))
+        xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
+        dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2)   # (B, K, H, W), channels_last strides
+        dw = torch.bmm(dheat, xn).sum(0, dtype=torch.float32).view(w_shape)
+        db = dheat.sum(dim=(0, 2), dtype=torch.float32)
+        return dx.to(x_dtype), dw.to(w_dtype), db.to(b_dtype), None, None, None
+
+
+def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth, return_coords=False):
+    """JointLocationLoss(final_layer(x), ...) for training without ever storing the (B, J*D, H, W) heat-map:
+    main/model.py:42 + main/train.py:67-71 as two tensor-core launches (K3, K4) plus library GEMMs for dW / dX."""
+    _require_cuda(x, "x")
+    B, J = gt_coord.shape[0], gt_coord.shape[1]
+    dev = x.device
+    gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
+    vis = _f32(gt_vis, dev, (B, J), "gt_vis")
+    hd = _f32(gt_have_depth, dev, (B, 1), "gt_have_depth")
+    if bias is None:
+        bias = torch.zeros(weight.shape[0], device=dev)
+    loss, coords = _FusedHeadIntegralL1.apply(x, weight, bias, gt, vis, hd)
+    return (loss, coords) if return_coords else loss
+
+
 def last_launch_count():
     return lib().ihpr_last_launch_count()
 

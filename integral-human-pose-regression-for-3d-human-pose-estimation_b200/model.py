@@ -7,8 +7,10 @@ contract `north_star` asks for: without a target it returns the heat-map exactly
 (model.py:99-103); with `target = {'coord', 'vis', 'have_depth'}` it returns the integral L1 loss computed by the
 sm_100a path (what main/train.py:64-67 does in two calls).
 """
+import torch
 import torch.nn as nn
 
+from .functional import fused_head_integral_l1_loss, fused_head_soft_argmax
 from .nets.loss import JointLocationLoss, soft_argmax
 from .nets.resnet import ResNetBackbone
 
@@ -41,14 +43,21 @@ class HeadNet(nn.Module):
 
 
 class ResPoseNet(nn.Module):
-    def __init__(self, backbone, head, joint_num=None):
+    def __init__(self, backbone, head, joint_num=None, fused_head=False):
+        """fused_head=True: final_layer + soft-argmax (+ loss) run as the tensor-core kernels K3 / K4 and the
+        (B, J*D, H, W) heat-map is never stored (same parameters, same checkpoints)."""
         super().__init__()
         self.backbone = backbone
         self.head = head
         self.joint_num = joint_num
+        self.fused_head = fused_head
         self.criterion = JointLocationLoss()
 
     def forward(self, input_img, target=None):
+        if target is not None and self.fused_head:
+            feat = self.head.deconv_layers(self.backbone(input_img))
+            fl = self.head.final_layer
+            return fused_head_integral_l1_loss(feat, fl.weight, fl.bias, target["coord"], target["vis"], target["have_depth"])
         heatmap = self.head(self.backbone(input_img))
         if target is None:
             return heatmap                             # reference contract, model.py:99-103
@@ -56,14 +65,18 @@ class ResPoseNet(nn.Module):
 
     def predict(self, input_img):
         """Inference: (B, J, 3) voxel coordinates, i.e. main/test.py:62-65 without the full-heat-map gather."""
+        if self.fused_head and not torch.is_grad_enabled():
+            feat = self.head.deconv_layers(self.backbone(input_img))
+            fl = self.head.final_layer
+            return fused_head_soft_argmax(feat, fl.weight, fl.bias, self.joint_num)
         return soft_argmax(self.forward(input_img), self.joint_num)
 
 
-def get_pose_net(cfg, is_train, joint_num):
+def get_pose_net(cfg, is_train, joint_num, fused_head=False):
     """model.py:105-114.  `cfg` needs `resnet_type` and `depth_dim` (main/config.py:24,28)."""
     backbone = ResNetBackbone(cfg.resnet_type)
     head = HeadNet(joint_num, depth_dim=cfg.depth_dim, inplanes=backbone.out_channels)
     if is_train:
         backbone.init_weights()
         head.init_weights()
-    return ResPoseNet(backbone, head, joint_num)
+    return ResPoseNet(backbone, head, joint_num, fused_head=fused_head)

@@ -362,3 +362,36 @@ def test_fused_head_conv_soft_argmax(case, dev):
     assert np.abs(lse - (m64 + np.log(l64))).max() <= 1e-3
     with pytest.raises(ihpr_b200.IhprError):            # forward-only
         ihpr_b200.fused_head_soft_argmax(xd.requires_grad_(True), wt.to(dev), bias.to(dev), J)
+
+
+@pytest.mark.parametrize("case", [(2, 18, 64, 64, 64, 256), (3, 5, 32, 32, 32, 128)])
+def test_fused_head_training_step(case, dev):
+    """K3 + K4: loss and parameter / activation gradients of final_layer + JointLocationLoss without a stored heat-map,
+    vs torch autograd through conv2d (fp32, same bf16-rounded operands) + the reference criterion restatement.
+    The heat-map gradient is emitted in bf16 (2^-9 relative rounding per element), hence the 2e-2 bounds."""
+    import ihpr_b200
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    B, J, D, H, W, K = case
+    g = torch.Generator(device="cpu").manual_seed(7 + B)
+    x = torch.randn(B, K, H, W, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(J * D, K, 1, 1, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(J * D, generator=g) * 0.5
+    gt, vis, hd = (torch.from_numpy(a) for a in inputs.make_targets(B, J, D, H, W, 3, "rand", "alt"))
+    # reference on the GPU in fp32
+    xr = x.float().to(dev).requires_grad_(True)
+    wr = wt.float().to(dev).requires_grad_(True)
+    br = bias.to(dev).requires_grad_(True)
+    heat = torch.nn.functional.conv2d(xr, wr, br)
+    loss_ref = RefJointLocationLoss()(heat, gt.to(dev), vis.to(dev), hd.to(dev)) * 1.5
+    loss_ref.backward()
+    # ours
+    xo = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wo = wt.to(dev).requires_grad_(True)
+    bo = bias.to(dev).requires_grad_(True)
+    loss = ihpr_b200.fused_head_integral_l1_loss(xo, wo, bo, gt.to(dev), vis.to(dev), hd.to(dev))
+    (loss * 1.5).backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() * 1.5 - loss_ref.item()) <= 2e-4 * max(1.0, abs(loss_ref.item()))
+    for ours, ref, name in ((xo.grad.float(), xr.grad, "dx"), (wo.grad.float(), wr.grad, "dw"), (bo.grad.float(), br.grad, "dbias")):
+        err = (ours - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= 2e-2, (name, err)

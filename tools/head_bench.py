@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""tools/head_bench.py -- K3 (fused 1x1 conv + soft-argmax, tcgen05) vs the unfused tail (cuDNN/cuBLAS conv in bf16
+channels_last writing the heat-map, then K1 reading it).  CUDA events, median of `iters`."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ihpr_b200
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=64)
+ap.add_argument("--J", type=int, default=18)
+ap.add_argument("--D", type=int, default=64)
+ap.add_argument("--K", type=int, default=256)
+ap.add_argument("--hw", type=int, default=64)
+ap.add_argument("--iters", type=int, default=20)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+B, J, D, K, H, W = a.B, a.J, a.D, a.K, a.hw, a.hw
+x = torch.randn(B, K, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+conv = torch.nn.Conv2d(K, J * D, 1).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+torch.nn.init.normal_(conv.weight, std=0.05)
+wt, bias = conv.weight.detach(), conv.bias.detach().float()
+torch.backends.cudnn.benchmark = True
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.iters)]
+    for s, e in ev:
+        s.record(); fn(); e.record()
+    torch.cuda.synchronize()
+    return sorted(s.elapsed_time(e) for s, e in ev)[a.iters // 2] * 1e3
+
+
+with torch.no_grad():
+    wb = wt.reshape(J * D, K).contiguous()
+    t_fused = timeit(lambda: ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J))
+    t_conv = timeit(lambda: conv(x))
+    heat = conv(x)
+    t_k1 = timeit(lambda: ihpr_b200.soft_argmax(heat, J))
+    t_unf = timeit(lambda: ihpr_b200.soft_argmax(conv(x), J))
+    c1 = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J)
+    c2 = ihpr_b200.soft_argmax(conv(x).float(), J)
+flop = 2.0 * B * J * D * K * H * W
+print(json.dumps({"B": B, "J": J, "D": D, "K": K, "HW": H, "fused_us": round(t_fused, 1), "fused_TFLOPs": round(flop / t_fused / 1e6, 1),
+                  "conv_us": round(t_conv, 1), "k1_bf16_us": round(t_k1, 1), "conv_plus_k1_us": round(t_unf, 1),
+                  "speedup": round(t_unf / t_fused, 2), "max_coord_diff_vs_unfused": float((c1 - c2).abs().max())}))
