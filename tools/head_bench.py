@@ -42,8 +42,23 @@ with torch.no_grad():
     t_k1 = timeit(lambda: ihpr_b200.soft_argmax(heat, J))
     t_unf = timeit(lambda: ihpr_b200.soft_argmax(conv(x), J))
     c1 = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J)
+# K4: heat-map gradient straight from the TMEM recompute
+from ihpr_b200._lib import lib, check
+from oracle import inputs as _inp
+gt, vis, hd = (torch.from_numpy(t).to(dev) for t in _inp.make_targets(B, J, D, H, W, 0))
+vis = vis.reshape(B, J).contiguous()
+with torch.no_grad():
+    coords, stats = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J, return_stats=True)
+go = torch.ones((), device=dev)
+dheat = torch.empty(B, J * D, H * W, dtype=torch.bfloat16, device=dev)
+stream = torch.cuda.current_stream().cuda_stream
+t_k4 = timeit(lambda: check(lib().ihpr_head_integral_l1_bwd(x.data_ptr(), wb.data_ptr(), bias.data_ptr(), B, K, J, D, H, W, coords.data_ptr(),
+                                                            stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), go.data_ptr(),
+                                                            dheat.data_ptr(), stream)))
+with torch.no_grad():
     c2 = ihpr_b200.soft_argmax(conv(x).float(), J)
 flop = 2.0 * B * J * D * K * H * W
 print(json.dumps({"B": B, "J": J, "D": D, "K": K, "HW": H, "fused_us": round(t_fused, 1), "fused_TFLOPs": round(flop / t_fused / 1e6, 1),
+                  "k4_bwd_us": round(t_k4, 1), "k4_TFLOPs": round(flop / t_k4 / 1e6, 1), "k4_write_GBps": round(B * J * D * H * W * 2 / t_k4 / 1e3, 1),
                   "conv_us": round(t_conv, 1), "k1_bf16_us": round(t_k1, 1), "conv_plus_k1_us": round(t_unf, 1),
                   "speedup": round(t_unf / t_fused, 2), "max_coord_diff_vs_unfused": float((c1 - c2).abs().max())}))

@@ -33,7 +33,7 @@ def main():
         h = rows[1]
         isrc, isamp, iexec = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
         sc = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
-        data = [r for r in rows[2:] if len(r) == len(h)]
+        data = [r for r in rows[2:] if len(r) == len(h) and (r[isamp] or '0').isdigit()]
         tot = sum(int(r[isamp] or 0) for r in data)
         print("--- hottest SASS lines of %s (samples, executed, top stalls); total samples %d, instructions %d" % (pat, tot, sum(int(r[iexec] or 0) for r in data)))
         for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:25]:
