@@ -348,6 +348,27 @@ def run_b200(args):
 TRAIN_GFLOP_PER_SAMPLE = {50: 50.55, 152: 108.7}      # conv/deconv MACs x 2, train = 3 x forward, J=18
 
 
+def EagerJointLocationLoss():
+    """What the reference executes on a GPU for its criterion (common/nets/loss.py:13-52): eager ATen ops, autograd
+    backward.  Only the `--workload train --torch-loss` comparison arm uses it, to put the e2e gain of the hot path in context."""
+    import torch
+
+    class _Eager(torch.nn.Module):
+        def forward(self, heat, gt, vis, have_depth):
+            J = gt.shape[1]
+            B, C, H, W = heat.shape
+            D = C // J
+            p = torch.softmax(heat.reshape(B, J, D * H * W), 2).reshape(B, J, D, H, W)
+            ax, ay, az = p.sum(dim=(2, 3)), p.sum(dim=(2, 4)), p.sum(dim=(3, 4))
+            dev = heat.device
+            x = (ax * torch.arange(1, W + 1, device=dev, dtype=torch.float32)).sum(2, keepdim=True) - 1
+            y = (ay * torch.arange(1, H + 1, device=dev, dtype=torch.float32)).sum(2, keepdim=True) - 1
+            z = (az * torch.arange(1, D + 1, device=dev, dtype=torch.float32)).sum(2, keepdim=True) - 1
+            loss = torch.abs(torch.cat((x, y, z), 2) - gt) * vis
+            return ((loss[:, :, 0] + loss[:, :, 1] + loss[:, :, 2] * have_depth) / 3.).mean()
+    return _Eager()
+
+
 def run_train(args):
     """BASELINE.json configs[1..3]: ResNet-50 + deconv head + integral loss, synthetic 256x256, B=32 per GPU,
     one process per GPU, NCCL gradient all-reduce (torch DDP).  Backbone/head are stock PyTorch + cuDNN (out of the
@@ -377,8 +398,7 @@ def run_train(args):
     net = get_pose_net(cfg, True, J, fused_head=args.fused_head)
     crit = None
     if args.torch_loss:
-        from oracle.soft_argmax_ref import RefJointLocationLoss     # comparison arm only: the reference's eager loss on the GPU
-        crit = RefJointLocationLoss()
+        crit = EagerJointLocationLoss()          # comparison arm only: the reference's eager op sequence on the GPU
     elif args.unfused_loss:
         crit = ihpr_b200.JointLocationLoss(fused_backward=False)
     tr = Trainer(net, cfg, criterion=crit, device=dev, autocast_dtype=torch.bfloat16 if args.precision == "bf16" else None,

@@ -24,8 +24,8 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return pol;
 }
 
-// Roles: warp 0 = TMA producer, warps 1..DEPTH+1 = exchangers (merge warp partials, trades CTA partials with the partner
-// CTAs, form the per-volume backward constants and write coords / stats / loss term), the last NCW warps = consumers.
+// Roles: warp 0 = TMA producer, warps 1..NCW = consumers, the last DEPTH+1 warps = exchangers (merge warp partials, trades CTA partials with the partner
+// CTAs, form the per-volume backward constants and write coords / stats / loss term).
 // The stream is software-pipelined by DEPTH units: consumers run pass1(u0..u_{DEPTH-1}), then alternate
 // pass1(u+DEPTH), pass2(u), so the exchange of unit u has DEPTH * (pass1 + pass2) - pass2 of time before its result
 // is needed; DEPTH + 1 units per CTA are live in L2.
@@ -98,12 +98,13 @@ __global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(c
         return;
     }
 
-    if (warp <= NB) {
-        // ================= exchangers: warp 1 + b serves the units u = b (mod NB) =================
+    if (warp > NCW) {
+        // ================= exchangers: warp NCW + 1 + b serves the units u = b (mod NB) =================
+        // (highest warp ids: the warp arbiter favours them, which shortens the exchange)
         // (one exchange costs a few loaded-L2 round trips, ~5 us, more than a unit takes to stream: NB of them run
         //  concurrently so that the exchange THROUGHPUT keeps up; the DEPTH-unit look-ahead hides the latency)
         const uint32_t tag = (uint32_t)__ldcg(p.epoch) + 1u;
-        const uint32_t b = warp - 1;
+        const uint32_t b = warp - (NCW + 1);
         for (uint32_t u = b; u < nunits; u += NB) {
             const uint32_t r = group + u * ngroups;
             const uint32_t ph = (u / NB) & 1;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(c
     constexpr int VPC = CHUNK_BYTES / 16;
     constexpr int U = (VPC / NC) < 1 ? 1 : ((VPC / NC) > 4 ? 4 : (VPC / NC));
     constexpr int QPV = Elem<T>::QPV;
-    const int tid = threadIdx.x - (NB + 1) * 32, wid = warp - (NB + 1);
+    const int tid = threadIdx.x - 32, wid = warp - 1;
     const bool fast = fast_ok<NC, VPC>(g);
     const uint32_t Fv = fast ? g.divFv.d : 1;
     const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NC / Fv), hf = u2f((uint32_t)g.H);

@@ -44,9 +44,8 @@ with torch.no_grad():
     c1 = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J)
 # K4: heat-map gradient straight from the TMEM recompute
 from ihpr_b200._lib import lib, check
-from oracle import inputs as _inp
-gt, vis, hd = (torch.from_numpy(t).to(dev) for t in _inp.make_targets(B, J, D, H, W, 0))
-vis = vis.reshape(B, J).contiguous()
+gt = torch.rand(B, J, 3, device=dev) * torch.tensor([W, H, D], device=dev, dtype=torch.float32)
+vis, hd = torch.ones(B, J, device=dev), torch.ones(B, 1, device=dev)
 with torch.no_grad():
     coords, stats = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J, return_stats=True)
 go = torch.ones((), device=dev)
