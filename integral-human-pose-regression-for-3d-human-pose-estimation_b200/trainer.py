@@ -64,7 +64,9 @@ class Trainer:
         self.raw_model = model
         if self.world > 1:
             ids = [self.device.index] if self.device.type == "cuda" else None
-            self.model = DDP(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=25)
+            # BN running statistics stay per rank, as in the reference's replicas (no SyncBN, balanced_parallel.py:16-43 is dead code)
+            self.model = DDP(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=25, broadcast_buffers=False,
+                             static_graph=True)
         else:
             self.model = model
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr)                       # base.py:75-77
