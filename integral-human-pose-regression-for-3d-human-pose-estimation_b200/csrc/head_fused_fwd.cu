@@ -32,7 +32,10 @@ namespace k3 {
 constexpr int BM = 128;             // channels per tile = UMMA M
 constexpr int BN = 256;             // pixels per tile   = UMMA N
 constexpr int BK = 64;              // k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int STAGES = 4;           // ring of X k-blocks
+constexpr int STAGES_FWD = 4;       // ring of X k-blocks (K3)
+constexpr int STAGES_BWD = 3;       // K4 gives one stage up for the gradient staging buffers
+constexpr int STG_ROW = 144;        // K4 staging: 64 bf16 (128 B) per channel row + 16 B pad (conflict-free 16-byte accesses)
+constexpr int STG_WARP = 32 * STG_ROW;
 constexpr int MAXKB = 4;            // K <= 256
 constexpr int A_KB_BYTES = BM * BK * 2;     // 16 KiB
 constexpr int B_KB_BYTES = BN * BK * 2;     // 32 KiB
@@ -100,6 +103,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 template <bool BWD>
 __global__ void __launch_bounds__(THREADS, 1)
 head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
+    constexpr int STAGES = BWD ? STAGES_BWD : STAGES_FWD;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -114,6 +118,8 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     uint64_t* t_empty = t_full + 2;         // [2]      epilogue -> MMA: accumulator stage drained (EPI_WARPS arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_WARPS][8]
+    // K4: [EPI_WARPS][32 rows][STG_ROW] gradient staging, 16-byte aligned
+    uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(red + 2 * EPI_WARPS) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.B * p.MT;
@@ -203,7 +209,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                 const float gz = sc * sgn(cz - __ldg(p.gt + 3 * r + 2)) * __ldg(p.have_depth + b);
                 const float k0 = bias2 - safe_c(m);
                 const float tz = gz * (zf - cz);
-                __nv_bfloat16* orow = p.grad_heat + ((size_t)b * p.J * p.D + c) * ((size_t)p.H * p.W);
+                uint8_t* wstg = stg + e * STG_WARP;
                 for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(t_full + as, aph);
@@ -223,10 +229,24 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                             const float d1 = ex2(fmaf(v[2 * i + 1], kLog2e, k0)) * fmaf((float)(2 * i + 1), gx, base);
                             o[i] = Elem<__nv_bfloat16>::pk(d0, d1);
                         }
-                        if (valid) {
-                            uint4* dst = reinterpret_cast<uint4*>(orow + pix);       // 32 pixels = 64 contiguous bytes of this channel row
+                        // this thread's 32 pixels (64 B) of its channel row go to the warp's staging tile ...
+                        uint8_t* srow = wstg + lane * STG_ROW + (j & 1) * 64;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) st_stream16(dst + i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                        for (int i = 0; i < 4; ++i)
+                            *reinterpret_cast<uint4*>(srow + i * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        if (j & 1) {
+                            // ... and every 64 pixels the tile leaves as full 128-byte lines: 8 lanes per channel row
+                            __syncwarp();
+                            const uint32_t pix0 = pix - 32;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = i * 4 + (lane >> 3);
+                                const int crow = mt * BM + qd * 32 + row;
+                                const uint4 val = *reinterpret_cast<const uint4*>(wstg + row * STG_ROW + (lane & 7) * 16);
+                                if (crow < p.J * p.D)
+                                    st_stream16(p.grad_heat + ((size_t)b * p.J * p.D + crow) * ((size_t)p.H * p.W) + pix0 + (lane & 7) * 8, val);
+                            }
+                            __syncwarp();
                         }
                     }
                     tc_fence_before();
@@ -356,7 +376,8 @@ const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bi
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
     if (!make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
-    const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + k3::STAGES * k3::B_KB_BYTES + 32 * sizeof(uint64_t) + 2 * k3::EPI_WARPS * 8 * sizeof(float);
+    const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + (bwd ? k3::STAGES_BWD : k3::STAGES_FWD) * k3::B_KB_BYTES + 32 * sizeof(uint64_t) +
+                        2 * k3::EPI_WARPS * 8 * sizeof(float) + (bwd ? k3::EPI_WARPS * k3::STG_WARP : 0);
     auto kern = bwd ? k3::head_softargmax_kernel<true> : k3::head_softargmax_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed";
     int grid = B * p.MT;
