@@ -273,24 +273,24 @@ int ihpr_scale_grad(void* grad_heat, int dtype, size_t n, const float* grad_out,
 }
 
 static int head_common(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, float* coords, float* stats,
-                       const float* gt, const float* vis, const float* hd, const float* grad_out, void* grad_heat, void* stream);
+                       const float* gt, const float* vis, const float* hd, const float* grad_out, void* grad_heat, float* dbias_part, void* stream);
 
 int ihpr_head_softargmax_fwd(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
                              float* stats, void* stream) {
-    return head_common(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    return head_common(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int ihpr_head_integral_l1_bwd(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, const float* coords,
                               const float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
-                              void* stream) {
+                              float* dbias_partial, void* stream) {
     if (!stats || !gt || !vis || !have_depth || !grad_out || !grad_heat) return fail(IHPR_EINVAL, "null argument");
     if ((uintptr_t)grad_heat & 15) return fail(IHPR_EINVAL, "grad_heat must be 16-byte aligned");
     return head_common(x_nhwc, weight, bias, B, K, J, D, H, W, const_cast<float*>(coords), const_cast<float*>(stats), gt, vis, have_depth, grad_out,
-                       grad_heat, stream);
+                       grad_heat, dbias_partial, stream);
 }
 
 static int head_common(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, float* coords, float* stats,
-                       const float* gt, const float* vis, const float* hd, const float* grad_out, void* grad_heat, void* stream) {
+                       const float* gt, const float* vis, const float* hd, const float* grad_out, void* grad_heat, float* dbias_part, void* stream) {
     g_launches = 0;
     if (!x_nhwc || !weight || !bias || !coords) return fail(IHPR_EINVAL, "null argument");
     if (B <= 0 || J <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
@@ -301,7 +301,7 @@ static int head_common(const void* x_nhwc, const void* weight, const float* bias
     int num_sms = 0;
     int rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
-    const char* err = ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, num_sms,
+    const char* err = ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part, num_sms,
                                               static_cast<cudaStream_t>(stream));
     if (err) return fail(IHPR_ECUDA, "%s", err);
     g_launches = 1;

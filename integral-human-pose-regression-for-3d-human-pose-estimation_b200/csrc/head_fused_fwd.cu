@@ -58,6 +58,7 @@ struct Params {
     const float* grad_out;  // device scalar
     float loss_scale;       // 1 / (3 * B * J)
     __nv_bfloat16* grad_heat;   // (B, J*D, H*W) bf16 out: d loss / d heat-map, the heat-map itself is only ever a TMEM tile
+    float* dbias_part;          // (B, 2, J*D) fp32 out or null: per-sample, per-column-half sums of the (unrounded) gradient = d loss / d bias partials
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -210,6 +211,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                 const float k0 = bias2 - safe_c(m);
                 const float tz = gz * (zf - cz);
                 uint8_t* wstg = stg + e * STG_WARP;
+                float dsum = 0.f;
                 for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(t_full + as, aph);
@@ -228,6 +230,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                             const float d0 = ex2(fmaf(v[2 * i], kLog2e, k0)) * fmaf((float)(2 * i), gx, base);
                             const float d1 = ex2(fmaf(v[2 * i + 1], kLog2e, k0)) * fmaf((float)(2 * i + 1), gx, base);
                             o[i] = Elem<__nv_bfloat16>::pk(d0, d1);
+                            dsum += d0 + d1;
                         }
                         // this thread's 32 pixels (64 B) of its channel row go to the warp's staging tile ...
                         uint8_t* srow = wstg + lane * STG_ROW + (j & 1) * 64;
@@ -253,6 +256,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + as);
                 }
+                if (p.dbias_part && valid) p.dbias_part[((size_t)b * 2 + ch) * (p.J * p.D) + c] = dsum;
                 continue;
             }
             // weights are 2^(acc*log2e + bias2 - cref); (m, c) of Acc hold the reference point of (acc + bias)
@@ -362,7 +366,7 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 
 const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
                               float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
-                              int num_sms, cudaStream_t s) {
+                              float* dbias_part, int num_sms, cudaStream_t s) {
     k3::Params p;
     p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
     p.MT = (J * D + k3::BM - 1) / k3::BM;
@@ -372,6 +376,7 @@ const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bi
     p.gt = gt; p.vis = vis; p.have_depth = have_depth; p.grad_out = grad_out;
     p.loss_scale = 1.0f / (3.0f * (float)B * (float)J);
     p.grad_heat = static_cast<__nv_bfloat16*>(grad_heat);
+    p.dbias_part = dbias_part;
     const bool bwd = grad_heat != nullptr;
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";

@@ -318,6 +318,6 @@ cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStrea
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
 const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
                               float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
-                              int num_sms, cudaStream_t s);
+                              float* dbias_part, int num_sms, cudaStream_t s);
 
 }  // namespace ihpr

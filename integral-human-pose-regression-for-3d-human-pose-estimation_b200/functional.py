@@ -329,16 +329,17 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         go = grad_loss.to(torch.float32).contiguous()
         dev = xb.device
         dheat = torch.empty((B, M, N), dtype=torch.bfloat16, device=dev)        # d loss / d heat-map, (B, J*D, H, W) layout
+        db_part = torch.empty((B, 2, M), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             check(lib().ihpr_head_integral_l1_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
                                                   coords.data_ptr(), stats.data_ptr(), gt.data_ptr(), vis.data_ptr(),
-                                                  hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), stream))
+                                                  hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), db_part.data_ptr(), stream))
         # conv backward = plain library GEMMs on the gradient (no layout changes: x is NHWC, dheat is (B, M, N))
         xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
         dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2)   # (B, K, H, W), channels_last strides
         dw = torch.bmm(dheat, xn).sum(0, dtype=torch.float32).view(w_shape)
-        db = dheat.sum(dim=(0, 2), dtype=torch.float32)
+        db = db_part.sum(dim=(0, 1))                                              # fixed-order sum of K4's per-sample partials
         return dx.to(x_dtype), dw.to(w_dtype), db.to(b_dtype), None, None, None
 
 

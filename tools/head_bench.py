@@ -53,7 +53,7 @@ dheat = torch.empty(B, J * D, H * W, dtype=torch.bfloat16, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 t_k4 = timeit(lambda: check(lib().ihpr_head_integral_l1_bwd(x.data_ptr(), wb.data_ptr(), bias.data_ptr(), B, K, J, D, H, W, coords.data_ptr(),
                                                             stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), go.data_ptr(),
-                                                            dheat.data_ptr(), stream)))
+                                                            dheat.data_ptr(), None, stream)))
 with torch.no_grad():
     c2 = ihpr_b200.soft_argmax(conv(x).float(), J)
 flop = 2.0 * B * J * D * K * H * W
