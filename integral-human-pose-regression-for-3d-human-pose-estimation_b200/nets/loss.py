@@ -57,26 +57,19 @@ class JointLocationLoss(nn.Module):
 
 
 class JointMSELoss(nn.Module):
-    """loss.py:55-84 (baseline regression criterion; not on the accelerated path)."""
+    """Criterion of the direct-regression baseline (loss.py:55-84; used by common/base.py:207), off the accelerated
+    path.  Same value as the reference's per-joint loop -- sum_j 0.5 * mean_{b,c}((w_bj * (pred_bjc - gt_bjc))^2) / J --
+    computed in one vectorised expression."""
 
     def __init__(self):
         super(JointMSELoss, self).__init__()
-        self.criterion = nn.MSELoss(reduction="mean")
         self.use_target_weight = True
 
     def forward(self, output, target, target_weight):
-        batch_size = target.size(0)
-        num_joints = target.size(1)
         _assert_no_grad(target)
         _assert_no_grad(target_weight)
-        coords_pred = output.reshape((batch_size, num_joints, -1)).split(1, 1)
-        coords_gt = target.reshape((batch_size, num_joints, -1)).split(1, 1)
-        loss = 0
-        for idx in range(num_joints):
-            coord_pred = coords_pred[idx].squeeze()
-            coord_gt = coords_gt[idx].squeeze()
-            if self.use_target_weight:
-                loss += 0.5 * self.criterion(coord_pred.mul(target_weight[:, idx]), coord_gt.mul(target_weight[:, idx]))
-            else:
-                loss += 0.5 * self.criterion(coord_pred, coord_gt)
-        return loss / num_joints
+        batch, joints = target.size(0), target.size(1)
+        diff = output.reshape(batch, joints, -1) - target.reshape(batch, joints, -1)
+        if self.use_target_weight:
+            diff = diff * target_weight.reshape(batch, joints, 1)
+        return 0.5 * diff.pow(2).mean(dim=(0, 2)).sum() / joints

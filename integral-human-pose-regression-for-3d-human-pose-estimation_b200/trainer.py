@@ -69,7 +69,8 @@ class Trainer:
                              static_graph=True)
         else:
             self.model = model
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr)                       # base.py:75-77
+        # base.py:75-77 (Adam, lr from the config); the fused multi-tensor implementation when the parameters are on a GPU
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(cfg.lr_dec_epoch),
                                                               gamma=cfg.lr_dec_factor)               # base.py:83-85
         self.autocast_dtype = autocast_dtype
