@@ -253,7 +253,19 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.S = S;
     p.loss_scale = scale;
     p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;
-    IHPR_CUDA(ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream)));
+    const cudaError_t le = ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream));
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+        // the S CTAs of a joint-volume cannot be made co-resident right now (GPU shared with other work): same result
+        // from the two-kernel path (still CUDA, still this library)
+        (void)cudaGetLastError();
+        rc = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        rc = bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, nullptr, scale, grad_heat, stream, 1.0f, true);
+        if (rc) return rc;
+        g_launches = 2;
+        return IHPR_OK;
+    }
+    IHPR_CUDA(le);
     g_launches = 1;
     IHPR_CUDA(cudaGetLastError());
     return IHPR_OK;

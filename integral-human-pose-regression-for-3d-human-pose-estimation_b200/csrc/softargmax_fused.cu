@@ -356,8 +356,8 @@ cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStrea
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s) {
     const size_t epv = dtype == 0 ? 4 : 8;
     const size_t n_vec = aligned ? n / epv : 0;
-    if (dtype == 0) scale_kernel<float><<<num_sms * 4, 512, 0, s>>>(static_cast<float*>(grad), n_vec, n_vec * epv, n, grad_out);
-    else scale_kernel<__nv_bfloat16><<<num_sms * 4, 512, 0, s>>>(static_cast<__nv_bfloat16*>(grad), n_vec, n_vec * epv, n, grad_out);
+    if (dtype == 0) scale_kernel<float><<<num_sms * 2, 256, 0, s>>>(static_cast<float*>(grad), n_vec, n_vec * epv, n, grad_out);
+    else scale_kernel<__nv_bfloat16><<<num_sms * 2, 256, 0, s>>>(static_cast<__nv_bfloat16*>(grad), n_vec, n_vec * epv, n, grad_out);
 }
 
 }  // namespace ihpr

@@ -53,6 +53,19 @@ def test_argument_validation_without_gpu(built_lib):
     assert rc == -1 and b"non-positive" in L.ihpr_last_error()
 
 
+def test_fused_head_argument_validation_without_gpu(built_lib):
+    from ihpr_b200._lib import lib
+    L = lib()
+    one = 1     # any non-null pointer: validation happens before anything is dereferenced
+    assert L.ihpr_head_softargmax_fwd(None, None, None, 1, 256, 18, 64, 64, 64, None, None, None) == -1
+    assert L.ihpr_head_softargmax_fwd(16, 16, 16, 1, 200, 18, 64, 64, 64, 16, None, None) == -1 and b"multiple of 64" in L.ihpr_last_error()
+    assert L.ihpr_head_softargmax_fwd(16, 16, 16, 1, 256, 18, 48, 64, 64, 16, None, None) == -1 and b"depth_dim" in L.ihpr_last_error()
+    assert L.ihpr_head_softargmax_fwd(16, 16, 16, 1, 256, 18, 64, 60, 60, 16, None, None) == -1 and b"W %" in L.ihpr_last_error()
+    assert L.ihpr_head_integral_l1_bwd(16, 16, 16, 1, 256, 18, 64, 64, 64, 16, None, None, None, None, None, None, None, None) == -1
+    assert L.ihpr_integral_l1_fwd_bwd(None, 0, 1, 2, 4, 4, 4, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.ihpr_scale_grad(None, 0, 16, None, None) == -1
+
+
 def test_missing_library_fails_loudly(monkeypatch, built_lib):
     from ihpr_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
