@@ -358,6 +358,19 @@ def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth
     return (loss, coords) if return_coords else loss
 
 
+def flip_merge(coord_out, flipped_coord_out, width, flip_pairs):
+    """Flip-test merge of main/test.py:67-76 on the (B, J, 3) coordinates (device tensors, no host round trip):
+    mirror x of the flipped pass (x' = W - x - 1), swap the left/right joints, average with the un-flipped pass."""
+    f = flipped_coord_out.clone()
+    f[:, :, 0] = width - f[:, :, 0] - 1
+    if len(flip_pairs):
+        idx = torch.arange(f.shape[1], device=f.device)
+        for a, b in flip_pairs:
+            idx[a], idx[b] = b, a
+        f = f[:, idx, :]
+    return (coord_out + f) / 2.
+
+
 def last_launch_count():
     return lib().ihpr_last_launch_count()
 

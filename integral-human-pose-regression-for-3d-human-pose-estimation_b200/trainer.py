@@ -49,6 +49,20 @@ def synthetic_batch(batch, joint_num, cfg, device, seed, pin=False):
     return [t.to(device, non_blocking=True) for t in out] if device is not None else out
 
 
+def stage_targets(joint_img, joint_vis, joints_have_depth, device):
+    """One pinned record and ONE host->device copy for the three target tensors of a batch (data/dataset.py:146-152 hands
+    them over separately and main/train.py:57-59 copies them one by one).  Returns device views (coord (B,J,3),
+    vis (B,J,1), have_depth (B,1)) into the single staged buffer; the C-ABI takes them as plain pointers."""
+    B, J = joint_img.shape[0], joint_img.shape[1]
+    n = B * J * 3 + B * J + B
+    host = torch.empty(n, dtype=torch.float32, pin_memory=(device.type == "cuda"))
+    host[:B * J * 3] = joint_img.reshape(-1)
+    host[B * J * 3:B * J * 4] = joint_vis.reshape(-1)
+    host[B * J * 4:] = joints_have_depth.reshape(-1)
+    dev = host.to(device, non_blocking=True)
+    return dev[:B * J * 3].view(B, J, 3), dev[B * J * 3:B * J * 4].view(B, J, 1), dev[B * J * 4:].view(B, 1)
+
+
 class Trainer:
     def __init__(self, model, cfg=DEFAULT_CFG, criterion=None, device=None, autocast_dtype=None, channels_last=False):
         self.cfg = cfg

@@ -66,3 +66,25 @@ def test_cfg_cross_check(built_lib, monkeypatch):
     with pytest.raises(ValueError, match="disagree with cfg"):
         loss._check_cfg(torch.zeros(1, 10, 2, 2), 2)
     loss._check_cfg(torch.zeros(1, 8, 2, 2), 2)
+
+
+def test_flip_merge_matches_reference_loop(built_lib):
+    """main/test.py:73-76 written as the reference does (in-place x mirror, pairwise clone-swap), against flip_merge"""
+    import ihpr_b200
+    torch.manual_seed(1)
+    W, pairs = 64, ((1, 4), (2, 5), (3, 6))
+    c, f = torch.rand(3, 8, 3) * 63, torch.rand(3, 8, 3) * 63
+    ref = f.clone()
+    ref[:, :, 0] = W - ref[:, :, 0] - 1
+    for pair in pairs:
+        ref[:, pair[0], :], ref[:, pair[1], :] = ref[:, pair[1], :].clone(), ref[:, pair[0], :].clone()
+    want = (c + ref) / 2.
+    assert torch.allclose(ihpr_b200.flip_merge(c, f, W, pairs), want)
+
+
+def test_stage_targets_views(built_lib):
+    from ihpr_b200.trainer import stage_targets
+    coord, vis, hd = torch.rand(4, 5, 3), torch.rand(4, 5, 1), torch.rand(4, 1)
+    c2, v2, h2 = stage_targets(coord, vis, hd, torch.device("cpu"))
+    assert torch.equal(c2, coord) and torch.equal(v2, vis) and torch.equal(h2, hd)
+    assert c2.data_ptr() + coord.numel() * 4 == v2.data_ptr()       # one buffer, back to back
