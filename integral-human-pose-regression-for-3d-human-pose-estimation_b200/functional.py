@@ -203,6 +203,8 @@ def soft_argmax(heatmaps, joint_num):
     assert isinstance(heatmaps, torch.Tensor)                    # loss.py:14
     _require_cuda(heatmaps, "heatmaps")
     _shape(heatmaps, joint_num)
+    if heatmaps.shape[0] == 0:                                   # empty batch: the reference returns an empty (0, J, 3) tensor
+        return heatmaps.new_zeros((0, joint_num, 3), dtype=torch.float32) + 0.0 * heatmaps.sum()
     return _SoftArgmax3D.apply(_normalise(heatmaps), int(joint_num))
 
 
@@ -219,6 +221,9 @@ def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords
     _shape(heatmap_out, J)
     if heatmap_out.shape[0] != B:
         raise ValueError("batch mismatch: heatmaps %d vs gt_coord %d" % (heatmap_out.shape[0], B))
+    if B == 0:                                                   # loss.py:52: mean() of an empty tensor is NaN
+        loss = heatmap_out.sum() * float("nan")
+        return (loss, heatmap_out.new_zeros((0, J, 3), dtype=torch.float32)) if return_coords else loss
     dev = heatmap_out.device
     gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
     vis = _f32(gt_vis, dev, (B, J), "gt_vis")

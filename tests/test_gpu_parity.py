@@ -122,6 +122,8 @@ def test_oracle_seeded_shapes(shape, dist, dev):
     (9, 17, 32, 64, 64, torch.float32),        # S = 2 (512 KiB joint-volumes)
     (10, 18, 64, 64, 64, torch.float32),       # S = 4 (1 MiB joint-volumes), the headline geometry
     (10, 18, 64, 64, 64, torch.bfloat16),      # S = 2 in bf16
+    (4, 18, 128, 64, 64, torch.float32),       # S = 16 (2 MiB joint-volumes, D = 128)
+    (6, 17, 48, 64, 64, torch.float32),        # 24 chunks per volume split 8 ways: 3 chunks per unit, J = 17
     (40, 8, 3, 5, 12, torch.float32),          # generic (non-fast) vector path inside K5
     (40, 8, 3, 5, 9, torch.float32),           # scalar shapes: falls back to K1 + K2
 ])
@@ -395,3 +397,29 @@ def test_fused_head_training_step(case, dev):
     for ours, ref, name in ((xo.grad.float(), xr.grad, "dx"), (wo.grad.float(), wr.grad, "dw"), (bo.grad.float(), br.grad, "dbias")):
         err = (ours - ref).abs().max().item() / ref.abs().max().item()
         assert err <= 2e-2, (name, err)
+
+
+def test_empty_batch_and_large_batch(dev):
+    """edge sizes: an empty batch behaves like the reference (empty coords, NaN mean); a 2.25 GiB batch (B=72, J=18, 64^3 fp32 --
+    joint-volume offsets beyond 2^31 bytes) keeps the invariants."""
+    import ihpr_b200
+    e = torch.zeros(0, 18 * 4, 8, 8, device=dev, requires_grad=True)
+    c = ihpr_b200.soft_argmax(e, 18)
+    assert c.shape == (0, 18, 3)
+    l = ihpr_b200.JointLocationLoss()(e, torch.zeros(0, 18, 3, device=dev), torch.zeros(0, 18, 1, device=dev), torch.zeros(0, 1, device=dev))
+    assert torch.isnan(l)
+    B, J, D, H, W = 72, 18, 64, 64, 64
+    gen = torch.Generator(device=dev).manual_seed(11)
+    h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
+    gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 0, "rand", "alt"))
+    for fused in (True, False):
+        h.grad = None
+        loss, coords = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True, fused_backward=fused)
+        loss.backward()
+        t = (coords - gt).abs() * vis.view(B, J, 1)
+        want = ((t[..., 0] + t[..., 1] + t[..., 2] * hd.view(B, 1)) / 3).mean()
+        assert abs(loss.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+        rows = h.grad.view(B * J, -1)
+        assert (rows.sum(1).abs() <= 1e-4 * rows.abs().sum(1).clamp_min(1e-30)).all()
+        hb = h.detach()[B - 1:].cpu().numpy()                       # the last sample lives past the 2 GiB mark
+        assert coord_err(coords[B - 1:].detach().cpu().numpy(), truth.soft_argmax_f64(hb, J)[0]) <= TOL
