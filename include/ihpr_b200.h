@@ -111,7 +111,7 @@ int ihpr_head_softargmax_fwd(const void *x_nhwc, const void *weight, const float
 /* Backward companion of ihpr_head_softargmax_fwd for training with the integral L1 loss: recomputes the heat-map
  * tile by tile on the tensor cores and writes d loss / d heat-map (bf16, (B, J*D, H, W) contiguous) from the coords /
  * stats the forward produced; grad_out is the device scalar d objective / d loss.  dbias_partial (may be NULL) receives
- * (B, 2, J*D) fp32 partial sums of the unrounded gradient: d loss / d bias = their sum over the first two axes.
+ * (B, 4, J*D) fp32 partial sums of the unrounded gradient: d loss / d bias = their sum over the first two axes.
  * The caller turns grad_heat into dW / dX with plain GEMMs (conv backward).  Together the two entries replace final_layer + criterion +
  * loss.backward() (main/train.py:64-71) without the heat-map ever being stored. */
 int ihpr_head_integral_l1_bwd(const void *x_nhwc, const void *weight, const float *bias,

@@ -12,11 +12,11 @@
 // sample run together and its X tiles come out of L2.  Per item the Wt tile (128 x K bf16, 64 KiB) is loaded once and
 // the 16 pixel tiles of X[b] stream through a 4-stage ring of 256 x 64 k-blocks.
 //
-// Epilogue (8 warps; warp%4 selects the TMEM lane quarter, warp/4 the column half): tcgen05.ld 32 columns at a time,
+// Epilogue (16 warps in K3, 8 in K4; warp%4 selects the TMEM lane quarter, warp/4 the column split): tcgen05.ld 32 columns at a time,
 // online softmax over pixels per lane with the same lazy re-base as K1, sum p, sum p*x, sum p*y per lane (z is the
 // lane's constant); after the last pixel tile the D lanes x 2 halves of a joint are merged and coords / stats written.
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4..11 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4.. = epilogue.
 //
 // K4 (template BWD = true) is the same GEMM with another epilogue: the heat-map tile is recomputed in TMEM, turned into
 // d loss / d heat = p * sum_c g_c (c(i) - coord_c) with the (m, l, coords) K3 saved, and written as bf16 in the heat-map's
@@ -34,13 +34,14 @@ constexpr int BN = 256;             // pixels per tile   = UMMA N
 constexpr int BK = 64;              // k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int STAGES_FWD = 4;       // ring of X k-blocks (K3)
 constexpr int STAGES_BWD = 3;       // K4 gives one stage up for the gradient staging buffers
-constexpr int STG_ROW = 144;        // K4 staging: 64 bf16 (128 B) per channel row + 16 B pad (conflict-free 16-byte accesses)
+constexpr int STG_ROW = 80;         // K4 staging: 32 bf16 (64 B) per channel row + 16 B pad (conflict-free 16-byte stores)
 constexpr int STG_WARP = 32 * STG_ROW;
 constexpr int MAXKB = 4;            // K <= 256
 constexpr int A_KB_BYTES = BM * BK * 2;     // 16 KiB
 constexpr int B_KB_BYTES = BN * BK * 2;     // 32 KiB
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 32 * (4 + EPI_WARPS);
+constexpr int EPI_FWD = 16;          // K3 epilogue warps: 4 per TMEM lane quarter, 64 columns each
+constexpr int EPI_BWD = 16;          // K4: also 4 per lane quarter -- its epilogue is latency-bound (TMEM load -> math -> staging -> store)
+constexpr int EPI_MAX = 16;
 constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 fp32 columns
 
 struct Params {
@@ -58,7 +59,7 @@ struct Params {
     const float* grad_out;  // device scalar
     float loss_scale;       // 1 / (3 * B * J)
     __nv_bfloat16* grad_heat;   // (B, J*D, H*W) bf16 out: d loss / d heat-map, the heat-map itself is only ever a TMEM tile
-    float* dbias_part;          // (B, 2, J*D) fp32 out or null: per-sample, per-column-half sums of the (unrounded) gradient = d loss / d bias partials
+    float* dbias_part;          // (B, 4, J*D) fp32 out or null: per-sample, per-column-split sums of the (unrounded) gradient = d loss / d bias partials
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -86,6 +87,31 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
         : "memory");
 }
+// Blackwell packed fp32 pairs (FFMA2 / FADD2 / FMUL2): two lanes of fp32 math per issue slot.  The epilogues are
+// issue-bound (ncu: the MMAs of a tile take fewer cycles than the epilogue needs issue slots), so every FMA / ADD over
+// the 32 columns a thread holds is done on (even, odd) column pairs.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -102,9 +128,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(32 * (4 + (BWD ? EPI_BWD : EPI_FWD)), 1)
 head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
     constexpr int STAGES = BWD ? STAGES_BWD : STAGES_FWD;
+    constexpr int EPI_WARPS = BWD ? EPI_BWD : EPI_FWD;
+    constexpr int CS = EPI_WARPS / 4;           // column splits of the 256-column accumulator stage
+    constexpr int CW = BN / CS;                 // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,9 +147,9 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     uint64_t* t_full = a_empty + 1;         // [2]      MMA -> epilogue: accumulator stage complete
     uint64_t* t_empty = t_full + 2;         // [2]      epilogue -> MMA: accumulator stage drained (EPI_WARPS arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_WARPS][8]
+    float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_MAX][8]
     // K4: [EPI_WARPS][32 rows][STG_ROW] gradient staging, 16-byte aligned
-    uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(red + 2 * EPI_WARPS) + 15) & ~(uintptr_t)15);
+    uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(red + 2 * EPI_MAX) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.B * p.MT;
@@ -188,7 +217,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
         // ================= epilogue =================
         const int e = warp - 4;
         const int qd = warp & 3;                 // TMEM lane quarter this warp may read
-        const int ch = e >> 2;                   // column half
+        const int ch = e >> 2;                   // column split
         const int lane_c = qd * 32 + lane;       // channel within the tile = TMEM lane
         const FastDiv divW = make_fastdiv((uint32_t)p.W);
         uint32_t acc_it = 0, n_item = 0;
@@ -216,47 +245,56 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(t_full + as, aph);
                     tc_fence_after();
-                    const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * (BN / 2);
+                    const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * CW;
 #pragma unroll 1
-                    for (int j = 0; j < BN / 2 / 32; ++j) {
+                    for (int j = 0; j < CW / 32; ++j) {
                         float v[32];
                         tmem_ld32(tbase + j * 32, v);
-                        const uint32_t pix = (uint32_t)(nt * BN + ch * (BN / 2) + j * 32);
+                        const uint32_t pix = (uint32_t)(nt * BN + ch * CW + j * 32);
                         const uint32_t y = fdiv(pix, divW);
                         const float base = fmaf(gy, u2f(y) - cy, fmaf(gx, u2f(pix - y * divW.d) - cx, tz));
                         uint32_t o[16];
+                        const uint64_t l2e2 = pk2(kLog2e, kLog2e), k02 = pk2(k0, k0);
+                        const uint64_t b01 = pk2(base, base + gx), gx22 = pk2(2.f * gx, 2.f * gx);
+                        uint64_t ds2 = pk2(0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float d0 = ex2(fmaf(v[2 * i], kLog2e, k0)) * fmaf((float)(2 * i), gx, base);
-                            const float d1 = ex2(fmaf(v[2 * i + 1], kLog2e, k0)) * fmaf((float)(2 * i + 1), gx, base);
+                            float t0, t1, d0, d1;
+                            up2(ffma2(pk2(v[2 * i], v[2 * i + 1]), l2e2, k02), t0, t1);
+                            // (base + 2i gx, base + (2i+1) gx) = (base, base + gx) + i (2gx, 2gx)
+                            const uint64_t dd = fmul2(pk2(ex2(t0), ex2(t1)), ffma2(pk2((float)i, (float)i), gx22, b01));
+                            ds2 = fadd2(ds2, dd);
+                            up2(dd, d0, d1);
                             o[i] = Elem<__nv_bfloat16>::pk(d0, d1);
-                            dsum += d0 + d1;
                         }
-                        // this thread's 32 pixels (64 B) of its channel row go to the warp's staging tile ...
-                        uint8_t* srow = wstg + lane * STG_ROW + (j & 1) * 64;
+                        {
+                            float da, db;
+                            up2(ds2, da, db);
+                            dsum += da + db;
+                        }
+                        // this thread's 32 pixels (64 B) of its channel row go to the warp's staging tile and leave as
+                        // 64-byte row segments, 4 lanes per channel row (the first version stored 16-byte pieces at an
+                        // 8 KiB stride straight from the registers: 154 us instead of 107 us at B = 32)
+                        uint8_t* srow = wstg + lane * STG_ROW;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             *reinterpret_cast<uint4*>(srow + i * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                        if (j & 1) {
-                            // ... and every 64 pixels the tile leaves as full 128-byte lines: 8 lanes per channel row
-                            __syncwarp();
-                            const uint32_t pix0 = pix - 32;
+                        __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int row = i * 4 + (lane >> 3);
-                                const int crow = mt * BM + qd * 32 + row;
-                                const uint4 val = *reinterpret_cast<const uint4*>(wstg + row * STG_ROW + (lane & 7) * 16);
-                                if (crow < p.J * p.D)
-                                    st_stream16(p.grad_heat + ((size_t)b * p.J * p.D + crow) * ((size_t)p.H * p.W) + pix0 + (lane & 7) * 8, val);
-                            }
-                            __syncwarp();
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2);
+                            const int crow = mt * BM + qd * 32 + row;
+                            const uint4 val = *reinterpret_cast<const uint4*>(wstg + row * STG_ROW + (lane & 3) * 16);
+                            if (crow < p.J * p.D)
+                                st_stream16(p.grad_heat + ((size_t)b * p.J * p.D + crow) * ((size_t)p.H * p.W) + pix + (lane & 3) * 8, val);
                         }
+                        __syncwarp();
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + as);
                 }
-                if (p.dbias_part && valid) p.dbias_part[((size_t)b * 2 + ch) * (p.J * p.D) + c] = dsum;
+                if (p.dbias_part && valid) p.dbias_part[((size_t)b * CS + ch) * (p.J * p.D) + c] = dsum;
                 continue;
             }
             // weights are 2^(acc*log2e + bias2 - cref); (m, c) of Acc hold the reference point of (acc + bias)
@@ -266,12 +304,12 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                 const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                 mbar_wait(t_full + as, aph);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * (BN / 2);
+                const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * CW;
 #pragma unroll 1
-                for (int j = 0; j < BN / 2 / 32; ++j) {
+                for (int j = 0; j < CW / 32; ++j) {
                     float v[32];
                     tmem_ld32(tbase + j * 32, v);
-                    const uint32_t pix = (uint32_t)(nt * BN + ch * (BN / 2) + j * 32);     // first pixel of this 32-column group
+                    const uint32_t pix = (uint32_t)(nt * BN + ch * CW + j * 32);     // first pixel of this 32-column group
                     const uint32_t y = fdiv(pix, divW);
                     const float yf = u2f(y), x0f = u2f(pix - y * divW.d);
                     float cmax = v[0];
@@ -282,13 +320,22 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     a.mx = fmaxf(a.mx, hmax);
                     if (hmax > a.lim) acc_raise(a, hmax);
                     const float k0 = bias2 - a.c;
-                    float s = 0.f, w = 0.f;
+                    // (even, odd) column pairs: s2 = (sum p_even, sum p_odd), w2 = (sum i p_2i, sum i p_2i+1)
+                    const uint64_t l2e2 = pk2(kLog2e, kLog2e), k02 = pk2(k0, k0);
+                    uint64_t s2a = pk2(0.f, 0.f), s2b = s2a, w2a = s2a, w2b = s2a;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float pw = ex2(fmaf(v[i], kLog2e, k0));
-                        s += pw;
-                        w = fmaf(pw, (float)i, w);
+                    for (int i = 0; i < 16; ++i) {
+                        float t0, t1;
+                        up2(ffma2(pk2(v[2 * i], v[2 * i + 1]), l2e2, k02), t0, t1);
+                        const uint64_t pp = pk2(ex2(t0), ex2(t1));
+                        if (i & 1) { s2b = fadd2(s2b, pp); w2b = ffma2(pp, pk2((float)i, (float)i), w2b); }
+                        else { s2a = fadd2(s2a, pp); w2a = ffma2(pp, pk2((float)i, (float)i), w2a); }
                     }
+                    float se, so, we, wo;
+                    up2(fadd2(s2a, s2b), se, so);
+                    up2(fadd2(w2a, w2b), we, wo);
+                    const float s = se + so;
+                    const float w = fmaf(2.f, we + wo, so);          // sum_j j p_j = 2 (sum i p_2i + sum i p_2i+1) + sum p_2i+1
                     a.l += s;
                     a.sx += fmaf(x0f, s, w);
                     a.sy = fmaf(yf, s, a.sy);
@@ -301,7 +348,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
             if (!valid) a.reset();
             a.sz = zf * a.l;
             a = acc_warp_merge(a);              // 32 lanes of one warp always belong to one joint (D % 32 == 0)
-            float(*rb)[8] = red + (n_item & 1) * EPI_WARPS;
+            float(*rb)[8] = red + (n_item & 1) * EPI_MAX;
             if (lane == 0) partial_to_smem(rb[e], a);
             named_bar_sync(1, EPI_WARPS * 32);
             const int jpt = BM / p.D;           // joints per channel tile
@@ -311,7 +358,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                 t.reset();
                 const int q0 = jt * p.D / 32, q1 = (jt + 1) * p.D / 32;       // lane quarters of this joint
                 for (int qq = q0; qq < q1; ++qq)
-                    for (int hh = 0; hh < 2; ++hh) t = acc_merge(t, partial_from_smem(rb[hh * 4 + qq]));
+                    for (int hh = 0; hh < CS; ++hh) t = acc_merge(t, partial_from_smem(rb[hh * 4 + qq]));
                 const int joint = mt * jpt + jt;
                 if (joint < p.J) {
                     const size_t r = (size_t)b * p.J + joint;
@@ -382,12 +429,12 @@ const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bi
     if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
     if (!make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
     const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + (bwd ? k3::STAGES_BWD : k3::STAGES_FWD) * k3::B_KB_BYTES + 32 * sizeof(uint64_t) +
-                        2 * k3::EPI_WARPS * 8 * sizeof(float) + (bwd ? k3::EPI_WARPS * k3::STG_WARP : 0);
+                        2 * k3::EPI_MAX * 8 * sizeof(float) + (bwd ? k3::EPI_BWD * k3::STG_WARP : 0);
     auto kern = bwd ? k3::head_softargmax_kernel<true> : k3::head_softargmax_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed";
     int grid = B * p.MT;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, k3::THREADS, smem, s>>>(map_w, map_x, p);
+    kern<<<grid, 32 * (4 + (bwd ? k3::EPI_BWD : k3::EPI_FWD)), smem, s>>>(map_w, map_x, p);
     return nullptr;
 }
 

@@ -334,7 +334,7 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         go = grad_loss.to(torch.float32).contiguous()
         dev = xb.device
         dheat = torch.empty((B, M, N), dtype=torch.bfloat16, device=dev)        # d loss / d heat-map, (B, J*D, H, W) layout
-        db_part = torch.empty((B, 2, M), dtype=torch.float32, device=dev)
+        db_part = torch.empty((B, 4, M), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             check(lib().ihpr_head_integral_l1_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
