@@ -14,7 +14,7 @@ namespace ihpr {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kGridCap = 2048;          // upper bound on persistent CTAs (workspace sizing)
-constexpr int kMaxSplit = 16;           // K5: at most this many CTAs share one joint-volume
+constexpr int kMaxSplit = 32;           // K5: at most this many CTAs share one joint-volume (one exchanger lane per partner)
 constexpr int kMinChunkElems = 2048;    // every kernel config streams chunks of >= this many voxels
 
 // ---------------------------------------------------------------------------------------------

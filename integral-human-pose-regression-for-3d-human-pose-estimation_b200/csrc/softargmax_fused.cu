@@ -13,6 +13,7 @@
 // DRAM traffic: read V + write V.  The producer warp never stops: pass-2 chunks of this unit and pass-1 chunks
 // of the next one are already in the ring while the consumers exchange partials.
 #include <cstdlib>
+#include <type_traits>
 
 #include "ihpr_device.cuh"
 
@@ -293,27 +294,29 @@ __global__ void scale_kernel(T* __restrict__ gh, size_t n_vec, size_t n_tail_sta
 }
 
 // Pipeline depth (units between pass 1 and pass 2 of the same unit) and unit size.  DEPTH + 1 units per CTA are live
-// in L2 between their two passes; tools/l2reuse.cu puts the cliff near 148 x 512 KiB.  Measured on B=32, J=18, 64^3
-// fp32 (profiles/r01_fused_sweep.txt): 128 KiB units (S = 8) with DEPTH 2 is the best point -- smaller units trade
-// too often (each exchange costs a few loaded-L2 round trips), deeper look-ahead spills out of L2.
-// IHPR_FUSED_DEPTH / IHPR_FUSED_SPLIT override the choice for tuning experiments.
-static int fused_depth() {
+// in L2 between their two passes (tools/l2reuse.cu puts the cliff near 148 x 512 KiB); every unit costs one exchange
+// (a few loaded-L2 round trips), so smaller units trade more often and deeper look-ahead spills out of L2.  The best
+// point was found by sweeping on B200 (profiles/r01_fused_sweep.txt): fp32 -> ~85 KiB units (S = 12 for 64^3, 6 for
+// 32x64x64, 24 for 128x64x64) with DEPTH 3; bf16 (twice the voxels, i.e. twice the math, per byte) -> 128 KiB units with
+// DEPTH 2.  IHPR_FUSED_DEPTH / IHPR_FUSED_SPLIT override the choice for tuning experiments.
+static int fused_depth(int dtype) {
     const char* e = getenv("IHPR_FUSED_DEPTH");
-    const int d = e ? atoi(e) : 2;
+    const int d = e ? atoi(e) : (dtype == 0 ? 3 : 2);
     return d < 1 ? 1 : (d > 3 ? 3 : d);
 }
 
 int fused_split(const Geometry& g, int dtype) {
     const uint64_t row_bytes = (uint64_t)g.N * (dtype == 0 ? 4 : 2);
+    int S;
     if (const char* e = getenv("IHPR_FUSED_SPLIT")) {
-        int S = atoi(e);
-        while (S > 1 && (uint32_t)S > g.nch) S /= 2;
-        return S < 1 ? 1 : (S > kMaxSplit ? kMaxSplit : S);
+        S = atoi(e);
+    } else {
+        const uint64_t target = (dtype == 0 ? 85u : 128u) << 10;
+        S = (int)((row_bytes + target / 2) / target);
     }
-    const uint64_t target = 128u << 10;
-    int S = 1;
-    while (row_bytes / S > target && S < kMaxSplit && (uint32_t)(2 * S) <= g.nch) S *= 2;
-    return S;
+    if (S > kMaxSplit) S = kMaxSplit;
+    if ((uint32_t)S > g.nch) S = (int)g.nch;
+    return S < 1 ? 1 : S;
 }
 
 template <typename T, int DEPTH>
@@ -342,7 +345,7 @@ static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_
 
 template <typename T>
 static cudaError_t launch_fused_t(const FusedParams& p, int num_sms, cudaStream_t s) {
-    switch (fused_depth()) {
+    switch (fused_depth(std::is_same<T, float>::value ? 0 : 1)) {
         case 1: return launch_fused_d<T, 1>(p, num_sms, s);
         case 2: return launch_fused_d<T, 2>(p, num_sms, s);
         default: return launch_fused_d<T, 3>(p, num_sms, s);

@@ -1,5 +1,5 @@
 // tools/kbench.cu -- Python-free timing of the C-ABI entry points (links lib/libihpr_b200.so).
-//   usage: kbench [variant] [B] [dtype 0|1] [iters]
+//   usage: kbench [variant] [B] [dtype 0|1] [iters] [D]
 // Prints back-to-back launch time (events around `iters` launches) for fwd, bwd, and fwd+bwd alternating.
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +33,8 @@ int main(int argc, char** argv) {
     int B = argc > 2 ? atoi(argv[2]) : 32;
     int dtype = argc > 3 ? atoi(argv[3]) : 0;
     int iters = argc > 4 ? atoi(argv[4]) : 20;
-    const int J = 18, D = 64, H = 64, W = 64;
+    const int D = argc > 5 ? atoi(argv[5]) : 64;
+    const int J = 18, H = 64, W = 64;
     const size_t R = (size_t)B * J, N = (size_t)D * H * W, es = dtype ? 2 : 4;
     void *heat, *grad, *ws; float *gt, *vis, *hd, *loss, *coords, *stats, *go;
     CK(cudaMalloc(&heat, R * N * es)); CK(cudaMalloc(&grad, R * N * es));
