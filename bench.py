@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--unfused-loss", action="store_true", help="train workload: K1 + K2 instead of K5")
     ap.add_argument("--fused-head", action="store_true", help="train workload: final_layer + loss as K3/K4 (heat-map never stored)")
+    ap.add_argument("--cuda-graph", action="store_true", help="train workload, 1 GPU: replay the whole step as one CUDA graph")
     ap.add_argument("--torch-loss", action="store_true", help="train workload: the reference's eager torch loss on the GPU (comparison arm)")
     return ap.parse_args()
 
@@ -418,6 +419,13 @@ def run_train(args):
         tr.train_step(*devb)
     torch.cuda.synchronize()
     K = args.steps
+    step_fn = tr.train_step
+    if args.cuda_graph and world == 1:
+        tr.capture(*devb)
+        step_fn = tr.graphed_step
+        for _ in range(3):
+            step_fn(*devb)
+        torch.cuda.synchronize()
 
     def timed(from_host):
         if world > 1:
@@ -429,7 +437,7 @@ def run_train(args):
         last = None
         for _ in range(K):
             batch = [t.to(dev, non_blocking=True) for t in host] if from_host else devb
-            last = tr.train_step(*batch)
+            last = step_fn(*batch)
             if from_host:
                 last = last.item()                       # device -> host read of the step's result
         e1.record()
@@ -463,7 +471,8 @@ def run_train(args):
                                    "DDP NCCL all-reduce" % (args.resnet, 4 * args.hw, 4 * args.hw, B, J, args.depth),
                        "criterion": "torch eager (reference ops)" if args.torch_loss else ("ihpr_b200 K1+K2" if args.unfused_loss else
                                      ("ihpr_b200 K3+K4 fused with final_layer" if args.fused_head else "ihpr_b200 K5")),
-                       "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark"},
+                       "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark",
+                       "launch": "one CUDA graph per step" if (args.cuda_graph and world == 1) else "eager"},
             "clocks": clocks,
             "e2e": {"value": world * B / wall_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": wall_e2e * 1e3,
                     "last_loss": last},

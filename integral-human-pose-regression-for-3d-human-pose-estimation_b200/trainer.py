@@ -84,7 +84,8 @@ class Trainer:
         else:
             self.model = model
         # base.py:75-77 (Adam, lr from the config); the fused multi-tensor implementation when the parameters are on a GPU
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"),
+                                          capturable=(self.device.type == "cuda"))
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(cfg.lr_dec_epoch),
                                                               gamma=cfg.lr_dec_factor)               # base.py:83-85
         self.autocast_dtype = autocast_dtype
@@ -105,6 +106,44 @@ class Trainer:
         loss.backward()
         self.optimizer.step()
         return loss.detach()
+
+    # ---- whole-step CUDA graph (single GPU): ~1200 launches per step become one graph replay ------------------------
+    def capture(self, input_img, joint_img, joint_vis, joints_have_depth, warmup=3):
+        """Capture forward + loss + backward + Adam step into one CUDA graph on static input buffers (PyTorch's
+        whole-network capture recipe).  The sm_100a ops are capture-safe: they only enqueue on the current stream,
+        take plain device pointers and allocate nothing themselves.  Afterwards `graphed_step(batch)` copies a batch
+        into the static buffers and replays.  Not combined with DDP here."""
+        assert self.world == 1 and self.device.type == "cuda"
+        self._static = [t.clone() for t in (input_img, joint_img, joint_vis, joints_have_depth)]
+        if self.channels_last:
+            self._static[0] = self._static[0].contiguous(memory_format=torch.channels_last)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_step(*self._static)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.model.train()
+        self.optimizer.zero_grad(set_to_none=True)
+        self._graph = torch.cuda.CUDAGraph()
+        target = {"coord": self._static[1], "vis": self._static[2], "have_depth": self._static[3]}
+        with torch.cuda.graph(self._graph):
+            if self.autocast_dtype is not None:
+                with torch.autocast(device_type="cuda", dtype=self.autocast_dtype):
+                    loss = self.model(self._static[0], target)
+            else:
+                loss = self.model(self._static[0], target)
+            loss.backward()
+            self.optimizer.step()
+        self._static_loss = loss.detach()
+        return self
+
+    def graphed_step(self, input_img, joint_img, joint_vis, joints_have_depth):
+        for dst, src in zip(self._static, (input_img, joint_img, joint_vis, joints_have_depth)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
 
     # ---- checkpoints in the reference's format ------------------------------------------------------------------
     def state(self):

@@ -423,3 +423,30 @@ def test_empty_batch_and_large_batch(dev):
         assert (rows.sum(1).abs() <= 1e-4 * rows.abs().sum(1).clamp_min(1e-30)).all()
         hb = h.detach()[B - 1:].cpu().numpy()                       # the last sample lives past the 2 GiB mark
         assert coord_err(coords[B - 1:].detach().cpu().numpy(), truth.soft_argmax_f64(hb, J)[0]) <= TOL
+
+
+def test_trainer_cuda_graph_matches_eager(dev):
+    """Whole-step CUDA graph (forward, K3/K4 fused head loss, backward, fused Adam): a replay computes the same loss as an eager
+    forward on the same parameters and batch, and it really applies the optimizer step.  (Step-by-step loss trajectories of two
+    separately trained tiny nets are not compared: cuDNN's non-deterministic reductions make them diverge within three steps.)"""
+    import types
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, synthetic_batch
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=32, input_shape=(128, 128), output_shape=(32, 32), lr=1e-3,
+                                lr_dec_epoch=[2, 3], lr_dec_factor=0.1, batch_size=4)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3, fused_head=True)
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.05)
+    tr = Trainer(net, cfg, device=dev)
+    b0, b1 = synthetic_batch(4, 3, cfg, dev, seed=0), synthetic_batch(4, 3, cfg, dev, seed=1)
+    tr.capture(*b0)
+    net.train()
+    with torch.no_grad():
+        want = net(b1[0], {"coord": b1[1], "vis": b1[2], "have_depth": b1[3]}).item()
+    w_before = net.head.final_layer.weight.detach().clone()
+    got = tr.graphed_step(*b1).item()
+    torch.cuda.synchronize()
+    assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (got, want)
+    assert not torch.equal(net.head.final_layer.weight, w_before)            # Adam stepped inside the graph
+    again = tr.graphed_step(*b1).item()
+    assert np.isfinite(again) and again != got
