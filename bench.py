@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
-    ap.add_argument("--slices", type=int, default=8)
+    ap.add_argument("--slices", type=int, default=16)
     ap.add_argument("--workload", default="path", choices=["path", "train"],
                     help="path: the soft-argmax/loss hot path (headline); train: ResNet + head + integral loss training step")
     ap.add_argument("--resnet", type=int, default=50)

@@ -153,8 +153,8 @@ struct HostCtx {
     size_t cap_heat = 0, cap_small = 0, cap_ws = 0;
     void *d_heat = nullptr, *d_grad = nullptr, *d_ws = nullptr;
     float* d_small = nullptr;       // gt, vis, hd, coords, stats, loss, grad_out
-    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ready = nullptr;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};     // [0] host->device copies, [1] kernels, [2] device->host copies
+    cudaEvent_t ev_in[64] = {}, ev_out[64] = {};                // per slice: input landed / gradient computed
 };
 std::mutex g_host_mu;
 HostCtx g_host[16];
@@ -331,6 +331,7 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
     if (device < 0 || device >= 16) return fail(IHPR_EINVAL, "device %d out of range", device);
     if (slices < 1) slices = 1;
     if (slices > B) slices = B;
+    if (slices > 64) slices = 64;
 
     std::lock_guard<std::mutex> lock(g_host_mu);
     int prev = -1;
@@ -347,7 +348,10 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
     if (c.device != device) {
         c.device = device;
         for (auto& s : c.streams) IHPR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        IHPR_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) {
+            IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+            IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
+        }
     }
     if (c.cap_heat < heat_bytes) {
         if (c.d_heat) cudaFree(c.d_heat);
@@ -363,13 +367,13 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
         IHPR_CUDA(cudaMalloc(&c.d_small, n_small * sizeof(float)));
         c.cap_small = n_small;
     }
-    if (c.cap_ws < 3 * ws_slice) {
+    if (c.cap_ws < ws_slice) {
         if (c.d_ws) cudaFree(c.d_ws);
         c.d_ws = nullptr; c.cap_ws = 0;
-        IHPR_CUDA(cudaMalloc(&c.d_ws, 3 * ws_slice));
-        c.cap_ws = 3 * ws_slice;
+        IHPR_CUDA(cudaMalloc(&c.d_ws, ws_slice));
+        c.cap_ws = ws_slice;
     }
-    IHPR_CUDA(cudaMemsetAsync(c.d_ws, 0, 3 * ws_slice, c.streams[0]));
+    IHPR_CUDA(cudaMemsetAsync(c.d_ws, 0, ws_slice, c.streams[0]));
     float* d_gt = c.d_small;
     float* d_vis = d_gt + R * 3;
     float* d_hd = d_vis + R;
@@ -383,9 +387,8 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
     IHPR_CUDA(cudaMemcpyAsync(d_vis, vis_host, R * sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
     IHPR_CUDA(cudaMemcpyAsync(d_hd, have_depth_host, B * sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
     IHPR_CUDA(cudaMemcpyAsync(d_go, &grad_out, sizeof(float), cudaMemcpyHostToDevice, c.streams[0]));
-    IHPR_CUDA(cudaEventRecord(c.ready, c.streams[0]));
-    IHPR_CUDA(cudaStreamWaitEvent(c.streams[1], c.ready, 0));
-    IHPR_CUDA(cudaStreamWaitEvent(c.streams[2], c.ready, 0));
+    // one stream per role, chained by per-slice events: the host->device engine never waits for a device->host copy
+    cudaStream_t s_in = c.streams[0], s_k = c.streams[1], s_out = c.streams[2];
 
     const float scale = 1.0f / (3.0f * (float)B * (float)J);
     const int variant = g_variant.load(std::memory_order_relaxed);
@@ -397,31 +400,33 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
         const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
         const int Bs = b1 - b0;
         if (Bs <= 0) continue;
-        cudaStream_t st = c.streams[i % 3];
         const size_t r0 = (size_t)b0 * J;
         const size_t off = r0 * N * es, bytes = (size_t)Bs * J * N * es;
         char* dh = static_cast<char*>(c.d_heat) + off;
         char* dg = static_cast<char*>(c.d_grad) + off;
-        IHPR_CUDA(cudaMemcpyAsync(dh, static_cast<const char*>(heat_host) + off, bytes, cudaMemcpyHostToDevice, st));
-        rc = ihpr_softargmax3d_fwd(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, static_cast<char*>(c.d_ws) + (i % 3) * ws_slice,
-                                   ws_slice, st);
+        IHPR_CUDA(cudaMemcpyAsync(dh, static_cast<const char*>(heat_host) + off, bytes, cudaMemcpyHostToDevice, s_in));
+        IHPR_CUDA(cudaEventRecord(c.ev_in[i], s_in));
+        IHPR_CUDA(cudaStreamWaitEvent(s_k, c.ev_in[i], 0));
+        rc = ihpr_softargmax3d_fwd(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, c.d_ws, ws_slice, s_k);
         if (rc) return rc;
         ++launches;
         if (grad_heat_host) {
             rc = bwd_common(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, nullptr, d_gt + r0 * 3, d_vis + r0, d_hd + b0, d_go, scale,
-                            dg, st);
+                            dg, s_k);
             if (rc) return rc;
             ++launches;
-            IHPR_CUDA(cudaMemcpyAsync(static_cast<char*>(grad_heat_host) + off, dg, bytes, cudaMemcpyDeviceToHost, st));
+            IHPR_CUDA(cudaEventRecord(c.ev_out[i], s_k));
+            IHPR_CUDA(cudaStreamWaitEvent(s_out, c.ev_out[i], 0));
+            IHPR_CUDA(cudaMemcpyAsync(static_cast<char*>(grad_heat_host) + off, dg, bytes, cudaMemcpyDeviceToHost, s_out));
         }
     }
-    for (auto& s : c.streams) IHPR_CUDA(cudaStreamSynchronize(s));
-    loss_from_coords_kernel<<<1, 32, 0, c.streams[0]>>>(d_coords, d_gt, d_vis, d_hd, (int)R, J, d_loss);
+    loss_from_coords_kernel<<<1, 32, 0, s_k>>>(d_coords, d_gt, d_vis, d_hd, (int)R, J, d_loss);
     ++launches;
     IHPR_CUDA(cudaGetLastError());
-    IHPR_CUDA(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, c.streams[0]));
-    if (coords_host) IHPR_CUDA(cudaMemcpyAsync(coords_host, d_coords, R * 3 * sizeof(float), cudaMemcpyDeviceToHost, c.streams[0]));
-    IHPR_CUDA(cudaStreamSynchronize(c.streams[0]));
+    IHPR_CUDA(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    if (coords_host) IHPR_CUDA(cudaMemcpyAsync(coords_host, d_coords, R * 3 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    IHPR_CUDA(cudaStreamSynchronize(s_k));
+    IHPR_CUDA(cudaStreamSynchronize(s_out));
     g_launches = launches;
     return IHPR_OK;
 }
@@ -439,7 +444,7 @@ int ihpr_host_release(int device) {
     if (c.d_ws) cudaFree(c.d_ws);
     if (c.d_small) cudaFree(c.d_small);
     for (auto& s : c.streams) if (s) cudaStreamDestroy(s);
-    if (c.ready) cudaEventDestroy(c.ready);
+    for (int i = 0; i < 64; ++i) { if (c.ev_in[i]) cudaEventDestroy(c.ev_in[i]); if (c.ev_out[i]) cudaEventDestroy(c.ev_out[i]); }
     c = HostCtx();
     cudaSetDevice(prev);
     return IHPR_OK;
