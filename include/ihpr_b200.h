@@ -99,6 +99,24 @@ int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, i
  * ihpr_integral_l1_fwd_bwd into autograd's answer for an arbitrary upstream gradient.  n = B*J*D*H*W elements. */
 int ihpr_scale_grad(void *grad_heat, int dtype, size_t n, const float *grad_out, void *stream);
 
+/* Test-time post-processing of the (B, J, 3) soft-argmax result in one launch, all buffers on the device:
+ *   1. flip-test merge, main/test.py:67-76 -- coords_flipped (nullable = no flip test) is the soft_argmax of the
+ *      mirrored image: x' = W - x - 1, joint j takes the flipped pass's joint flip_perm[j] (nullable = identity;
+ *      the reference's pairwise swaps as a permutation), result (coords + flipped') / 2   -> merged_out;
+ *   2. warp_coord_to_original, common/utils/pose_utils.py:68-75 -- x / W * bbox_w + bbox_x, y / H * bbox_h + bbox_y,
+ *      (z / D * 2 - 1) * bbox3d_depth / 2 + center_cam.z                                      -> pixel_out;
+ *   3. pixel2cam, pose_utils.py:14-20 -- ((x - c) / f) * z                                    -> cam_out,
+ *   4. minus the root joint's camera coordinate when root_idx >= 0, data/Human36M/Human36M.py:226-228.
+ * bbox (B,4) = x, y, w, h; center_cam (B,3); focal, princpt (B,2); bbox3d_depth = cfg.bbox_3d_shape[0]
+ * (main/config.py:29, 2000 mm).  Each of the three outputs (B, J, 3) is optional (NULL); outputs must not alias
+ * inputs.  fp32 arithmetic in the reference's operation order (the reference mixes fp32 and fp64 in numpy:
+ * agreement is to fp32 rounding, ~1e-6 relative). */
+int ihpr_coords_to_camera(const float *coords, const float *coords_flipped, const int *flip_perm,
+                          int B, int J, int D, int H, int W,
+                          const float *bbox, const float *center_cam, const float *focal, const float *princpt,
+                          float bbox3d_depth, int root_idx,
+                          float *merged_out, float *pixel_out, float *cam_out, void *stream);
+
 /* HeadNet.final_layer (1x1 conv with bias, main/model.py:14-20,42) fused with soft_argmax (loss.py:13-34), forward:
  * coords of the heat-map  W x + b  without ever writing the heat-map (tcgen05 / TMEM GEMM with a soft-argmax epilogue).
  * x_nhwc: (B, H, W, K) bf16, i.e. the (B, K, H, W) activations in channels_last memory format; weight: (J*D, K) bf16

@@ -284,6 +284,29 @@ int ihpr_scale_grad(void* grad_heat, int dtype, size_t n, const float* grad_out,
     return IHPR_OK;
 }
 
+int ihpr_coords_to_camera(const float* coords, const float* coords_flipped, const int* flip_perm, int B, int J, int D, int H, int W, const float* bbox,
+                          const float* center_cam, const float* focal, const float* princpt, float bbox3d_depth, int root_idx, float* merged_out,
+                          float* pixel_out, float* cam_out, void* stream) {
+    g_launches = 0;
+    if (!coords) return fail(IHPR_EINVAL, "null argument");
+    if (B < 0 || J <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if (root_idx >= J) return fail(IHPR_EINVAL, "root_idx %d out of range for %d joints", root_idx, J);
+    if (!merged_out && !pixel_out && !cam_out) return fail(IHPR_EINVAL, "no output requested");
+    if ((pixel_out || cam_out) && (!bbox || !center_cam)) return fail(IHPR_EINVAL, "pixel / camera output needs bbox and center_cam");
+    if (cam_out && (!focal || !princpt)) return fail(IHPR_EINVAL, "camera output needs focal and princpt");
+    if (merged_out && (merged_out == coords || merged_out == coords_flipped)) return fail(IHPR_EINVAL, "merged_out must not alias an input");
+    if (B == 0) return IHPR_OK;
+    if ((long long)B * J > 0x7fffffffLL) return fail(IHPR_EINVAL, "B*J does not fit in 31 bits");
+    int num_sms = 0;
+    int rc = check_device(coords, &num_sms);
+    if (rc) return rc;
+    ihpr::launch_coords_post(coords, coords_flipped, flip_perm, B, J, D, H, W, bbox, center_cam, focal, princpt, bbox3d_depth, root_idx < 0 ? -1 : root_idx,
+                             merged_out, pixel_out, cam_out, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 static int head_common(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W, float* coords, float* stats,
                        const float* gt, const float* vis, const float* hd, const float* grad_out, void* grad_heat, float* dbias_part, void* stream);
 

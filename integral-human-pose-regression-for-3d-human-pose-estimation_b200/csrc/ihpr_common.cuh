@@ -316,6 +316,9 @@ Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok
 int fused_split(const Geometry& g, int dtype);
 cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s);
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
+void launch_coords_post(const float* coords, const float* flipped, const int* perm, int B, int J, int D, int H, int W, const float* bbox,
+                        const float* center, const float* focal, const float* princpt, float bbox3d_depth, int root, float* merged, float* pixel,
+                        float* cam, cudaStream_t s);
 const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
                               float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
                               float* dbias_part, int num_sms, cudaStream_t s);

@@ -363,17 +363,97 @@ def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth
     return (loss, coords) if return_coords else loss
 
 
+def flip_perm(joint_num, flip_pairs):
+    """The pairwise left/right swaps of main/test.py:74-75, applied in order, as one permutation:
+    after the swaps joint j holds what joint perm[j] held before."""
+    perm = list(range(joint_num))
+    for a, b in flip_pairs:
+        perm[a], perm[b] = perm[b], perm[a]
+    return perm
+
+
+_perm_cache = {}
+
+
+def _perm_tensor(joint_num, flip_pairs, dev):
+    key = (dev, joint_num, tuple((int(a), int(b)) for a, b in flip_pairs))
+    t = _perm_cache.get(key)
+    if t is None:
+        t = _perm_cache[key] = torch.tensor(flip_perm(joint_num, key[2]), dtype=torch.int32, device=dev)
+    return t
+
+
+def _coords_arg(t, name, dev=None):
+    _require_cuda(t, name)
+    if dev is not None and t.device != dev:
+        raise IhprError("%s is on %s but coord_out is on %s" % (name, t.device, dev))
+    return t.detach().to(torch.float32).contiguous()
+
+
+def coords_to_camera(coord_out, bbox=None, center_cam=None, f=None, c=None, root_idx=None, flipped_coord_out=None, flip_pairs=(),
+                     depth_dim=64, output_shape=(64, 64), bbox_3d_depth=2000.0, outputs=("merged", "pixel", "cam")):
+    """Test-time post-processing of the soft-argmax result in ONE launch (ihpr_coords_to_camera), nothing leaves the device:
+
+    * ``merged``: flip-test merge of ``coord_out`` with ``flipped_coord_out`` (main/test.py:67-76); a copy of ``coord_out`` without one;
+    * ``pixel``:  ``warp_coord_to_original`` (common/utils/pose_utils.py:68-75) with per-sample ``bbox`` (B,4) / ``center_cam`` (B,3);
+    * ``cam``:    ``pixel2cam`` (pose_utils.py:14-20) with per-sample ``f``, ``c`` (B,2), minus the root joint when ``root_idx`` is
+      given (data/Human36M/Human36M.py:226-228).
+
+    ``depth_dim`` / ``output_shape`` (H, W) / ``bbox_3d_depth`` are cfg.depth_dim, cfg.output_shape, cfg.bbox_3d_shape[0]
+    (main/config.py:27-29).  Returns a dict of (B, J, 3) fp32 device tensors for the requested ``outputs``."""
+    coords = _coords_arg(coord_out, "coord_out")
+    if coords.dim() != 3 or coords.shape[2] != 3:
+        raise ValueError("coord_out must be (B, J, 3), got %s" % (tuple(coords.shape),))
+    B, J, _ = coords.shape
+    dev = coords.device
+    bad = set(outputs) - {"merged", "pixel", "cam"}
+    if bad or not outputs:
+        raise ValueError("outputs must be a non-empty subset of merged / pixel / cam, got %r" % (tuple(outputs),))
+
+    def per_sample(t, width, name, needed):
+        if t is None:
+            if needed:
+                raise ValueError("%s is required for the requested outputs" % name)
+            return None
+        t = _coords_arg(torch.as_tensor(t, device=dev) if not isinstance(t, torch.Tensor) else t, name, dev)
+        if t.dim() == 1:                      # one camera / box for the whole batch
+            t = t.expand(B, width).contiguous()
+        if tuple(t.shape) != (B, width):
+            raise ValueError("%s has shape %s, expected (%d, %d)" % (name, tuple(t.shape), B, width))
+        return t
+
+    geo = "pixel" in outputs or "cam" in outputs
+    bbox = per_sample(bbox, 4, "bbox", geo)
+    center_cam = per_sample(center_cam, 3, "center_cam", geo)
+    f = per_sample(f, 2, "f", "cam" in outputs)
+    c = per_sample(c, 2, "c", "cam" in outputs)
+    flipped = perm = None
+    if flipped_coord_out is not None:
+        flipped = _coords_arg(flipped_coord_out, "flipped_coord_out", dev)
+        if flipped.shape != coords.shape:
+            raise ValueError("flipped_coord_out has shape %s, expected %s" % (tuple(flipped.shape), tuple(coords.shape)))
+        if len(flip_pairs):
+            perm = _perm_tensor(J, flip_pairs, dev)
+    root = -1 if root_idx is None else int(root_idx)
+    if root >= J:
+        raise ValueError("root_idx %d out of range for %d joints" % (root, J))
+    out = {k: torch.empty(B, J, 3, dtype=torch.float32, device=dev) for k in outputs}
+    if B == 0:
+        return out
+    ptr = lambda t: t.data_ptr() if t is not None else None     # noqa: E731
+    with torch.cuda.device(dev):
+        check(lib().ihpr_coords_to_camera(ptr(coords), ptr(flipped), ptr(perm), B, J, int(depth_dim), int(output_shape[0]), int(output_shape[1]),
+                                          ptr(bbox), ptr(center_cam), ptr(f), ptr(c), float(bbox_3d_depth), root,
+                                          ptr(out.get("merged")), ptr(out.get("pixel")), ptr(out.get("cam")),
+                                          torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
 def flip_merge(coord_out, flipped_coord_out, width, flip_pairs):
-    """Flip-test merge of main/test.py:67-76 on the (B, J, 3) coordinates (device tensors, no host round trip):
+    """Flip-test merge of main/test.py:67-76 on the (B, J, 3) device coordinates, one launch, no host round trip:
     mirror x of the flipped pass (x' = W - x - 1), swap the left/right joints, average with the un-flipped pass."""
-    f = flipped_coord_out.clone()
-    f[:, :, 0] = width - f[:, :, 0] - 1
-    if len(flip_pairs):
-        idx = torch.arange(f.shape[1], device=f.device)
-        for a, b in flip_pairs:
-            idx[a], idx[b] = b, a
-        f = f[:, idx, :]
-    return (coord_out + f) / 2.
+    return coords_to_camera(coord_out, flipped_coord_out=flipped_coord_out, flip_pairs=flip_pairs, output_shape=(1, int(width)),
+                            outputs=("merged",))["merged"]
 
 
 def last_launch_count():

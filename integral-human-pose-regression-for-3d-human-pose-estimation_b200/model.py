@@ -10,7 +10,7 @@ sm_100a path (what main/train.py:64-67 does in two calls).
 import torch
 import torch.nn as nn
 
-from .functional import fused_head_integral_l1_loss, fused_head_soft_argmax
+from .functional import flip_merge, fused_head_integral_l1_loss, fused_head_soft_argmax
 from .nets.loss import JointLocationLoss, soft_argmax
 from .nets.resnet import ResNetBackbone
 
@@ -63,13 +63,23 @@ class ResPoseNet(nn.Module):
             return heatmap                             # reference contract, model.py:99-103
         return self.criterion(heatmap, target["coord"], target["vis"], target["have_depth"])
 
-    def predict(self, input_img):
-        """Inference: (B, J, 3) voxel coordinates, i.e. main/test.py:62-65 without the full-heat-map gather."""
+    def predict(self, input_img, flip_pairs=None):
+        """Inference: (B, J, 3) voxel coordinates, i.e. main/test.py:62-65 without the full-heat-map gather.  With ``flip_pairs``
+        (cfg.flip_test, test.py:67-76) the mirrored image goes through the network as well and the two results are merged on the
+        device by one K6 launch."""
+        coords, width = self._coords(input_img)
+        if flip_pairs is None:
+            return coords
+        flipped, _ = self._coords(torch.flip(input_img, dims=(3,)))
+        return flip_merge(coords, flipped, width, flip_pairs)
+
+    def _coords(self, input_img):
         if self.fused_head and not torch.is_grad_enabled():
             feat = self.head.deconv_layers(self.backbone(input_img))
             fl = self.head.final_layer
-            return fused_head_soft_argmax(feat, fl.weight, fl.bias, self.joint_num)
-        return soft_argmax(self.forward(input_img), self.joint_num)
+            return fused_head_soft_argmax(feat, fl.weight, fl.bias, self.joint_num), feat.shape[3]
+        heatmap = self.forward(input_img)
+        return soft_argmax(heatmap, self.joint_num), heatmap.shape[3]
 
 
 def get_pose_net(cfg, is_train, joint_num, fused_head=False):

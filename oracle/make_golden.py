@@ -83,6 +83,48 @@ def main():
               f"{os.path.getsize(path)/1024:.0f} KiB")
 
 
+# name, B, J, D, H, W, seed, flip, pairs, root
+POST_CASES = [
+    ("post_h36m_b4j18_flip", 4, 18, 64, 64, 64, 21, True, ((1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13)), 0),
+    ("post_noflip_b3j17",    3, 17, 64, 64, 64, 22, False, (), 0),
+    ("post_odd_b2j5_d16h24w40_chain", 2, 5, 16, 24, 40, 23, True, ((0, 1), (1, 2)), 3),
+    ("post_noroot_b1j4",     1, 4, 32, 64, 64, 24, True, ((0, 3),), -1),
+]
+
+
+def make_post_goldens():
+    """tests/golden/post_*.npz: the reference's own warp_coord_to_original / pixel2cam (common/utils/pose_utils.py:68-75,14-20)
+    chained per sample as data/Human36M/Human36M.py:203-228 does; the flip merge (inline in main/test.py:73-76, not importable)
+    is oracle.coords_post_ref.flip_merge.  Pins oracle.coords_post_ref bit for bit while doing so."""
+    from oracle import coords_post_ref as cp
+    ref = Reference()
+    from utils.pose_utils import pixel2cam, warp_coord_to_original            # the reference's functions (scratch copy)
+    for name, B, J, D, H, W, seed, flip, pairs, root in POST_CASES:
+        coords, flipped, bbox, center, f, c = cp.make_inputs(B, J, D, H, W, seed, flip)
+        ref.set_shape(D, H, W)
+        depth = float(ref.cfg.bbox_3d_shape[0])
+        merged = coords if flipped is None else cp.flip_merge(torch.from_numpy(coords), torch.from_numpy(flipped), W, pairs).numpy()
+        pix = np.zeros_like(merged)
+        cam = np.zeros(merged.shape, np.float64)
+        for n in range(B):
+            p2 = merged[n].copy()
+            p2[:, 0], p2[:, 1], p2[:, 2] = warp_coord_to_original(p2, bbox[n], center[n])
+            p3 = np.zeros((J, 3))
+            p3[:, 0], p3[:, 1], p3[:, 2] = pixel2cam(p2, f[n], c[n])
+            if root >= 0:
+                p3 = p3 - p3[root]
+            pix[n], cam[n] = p2, p3
+        m2, pix2, cam2 = cp.post_process(coords, flipped, pairs, bbox, center, f, c, root, D, (H, W), depth)
+        assert np.array_equal(m2, merged) and np.array_equal(pix2, pix) and np.array_equal(cam2, cam), name
+        out = dict(B=B, J=J, D=D, H=H, W=W, seed=seed, flip=flip, pairs=np.array(pairs, np.int32).reshape(-1, 2), root=root,
+                   bbox_3d_depth=depth, coords=coords, bbox=bbox, center_cam=center, f=f, c=c, merged=merged, pixel=pix, cam=cam)
+        if flipped is not None:
+            out["flipped"] = flipped
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name:34s} |cam|max={np.abs(cam).max():.1f} {os.path.getsize(path)/1024:.1f} KiB")
+
+
 def dump_reference_state_keys():
     """state_dict keys + shapes of the reference's own get_pose_net (main/model.py:105-114) for ResNet-50 / J=18,
     as a fixture for the checkpoint-compatibility test of ihpr_b200.model (the reference's resnet.py imports
@@ -107,6 +149,10 @@ def dump_reference_state_keys():
 
 
 if __name__ == "__main__":
+    if "--post" in sys.argv:                 # only the post-processing fixtures
+        make_post_goldens()
+        sys.exit(0)
     if "--keys" not in sys.argv:
         main()
+        make_post_goldens()
     dump_reference_state_keys()

@@ -17,7 +17,21 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith("post_"))
+
+
+def post_golden_names():
+    """Fixtures of the test-time post-processing (K6), written by `python -m oracle.make_golden --post`."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "post_*.npz")))
+
+
+def load_post_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["pairs"] = tuple((int(a), int(b)) for a, b in g["pairs"])
+    for k in ("B", "J", "D", "H", "W", "root"):
+        g[k] = int(g[k])
+    g.setdefault("flipped", None)
+    return g
 
 
 def load_golden(name):

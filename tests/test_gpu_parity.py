@@ -336,6 +336,14 @@ def test_model_forward_input_target_contract(dev):
     assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
     assert (g_ours - g_ref).abs().max().item() <= 1e-3 * g_ref.abs().max().item()
     assert net.predict(x).shape == (3, 4, 3)
+    # flip test (main/test.py:67-76) through predict(): the same two passes merged by the oracle's restatement
+    from oracle.coords_post_ref import flip_merge as ref_flip_merge
+    net.eval()
+    with torch.no_grad():
+        pairs = ((0, 1), (2, 3))
+        merged = net.predict(x, flip_pairs=pairs)
+        want = ref_flip_merge(net.predict(x).cpu(), net.predict(torch.flip(x, dims=(3,))).cpu(), 16, pairs)
+    assert torch.equal(merged.cpu(), want)
 
 
 @pytest.mark.parametrize("case", [(2, 18, 64, 64, 64, 256), (3, 17, 64, 64, 64, 256), (2, 4, 32, 32, 32, 128), (1, 2, 128, 16, 32, 64)])

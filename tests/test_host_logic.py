@@ -68,18 +68,26 @@ def test_cfg_cross_check(built_lib, monkeypatch):
     loss._check_cfg(torch.zeros(1, 8, 2, 2), 2)
 
 
-def test_flip_merge_matches_reference_loop(built_lib):
-    """main/test.py:73-76 written as the reference does (in-place x mirror, pairwise clone-swap), against flip_merge"""
+def test_flip_perm_matches_reference_loop(built_lib):
+    """main/test.py:74-75 swaps joints pair by pair with clones; flip_perm must be that sequence as ONE permutation,
+    also when pairs share a joint (sequential swaps compose, they do not commute)."""
     import ihpr_b200
     torch.manual_seed(1)
-    W, pairs = 64, ((1, 4), (2, 5), (3, 6))
-    c, f = torch.rand(3, 8, 3) * 63, torch.rand(3, 8, 3) * 63
-    ref = f.clone()
-    ref[:, :, 0] = W - ref[:, :, 0] - 1
-    for pair in pairs:
-        ref[:, pair[0], :], ref[:, pair[1], :] = ref[:, pair[1], :].clone(), ref[:, pair[0], :].clone()
-    want = (c + ref) / 2.
-    assert torch.allclose(ihpr_b200.flip_merge(c, f, W, pairs), want)
+    for pairs in (((1, 4), (2, 5), (3, 6)), ((0, 1), (1, 2)), ((2, 2),), ()):
+        f = torch.rand(3, 8, 3)
+        ref = f.clone()
+        for pair in pairs:
+            ref[:, pair[0], :], ref[:, pair[1], :] = ref[:, pair[1], :].clone(), ref[:, pair[0], :].clone()
+        assert torch.equal(f[:, ihpr_b200.flip_perm(8, pairs), :], ref)
+
+
+def test_post_processing_has_no_cpu_path(built_lib):
+    import ihpr_b200
+    c = torch.rand(2, 4, 3)
+    with pytest.raises(ihpr_b200.IhprError):
+        ihpr_b200.flip_merge(c, c, 64, ((0, 1),))
+    with pytest.raises(ihpr_b200.IhprError):
+        ihpr_b200.coords_to_camera(c, bbox=torch.rand(2, 4), center_cam=torch.rand(2, 3), f=torch.rand(2, 2), c=torch.rand(2, 2))
 
 
 def test_stage_targets_views(built_lib):

@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden
-from oracle import inputs, truth
+from conftest import golden_names, load_golden, load_post_golden, post_golden_names
+from oracle import coords_post_ref, inputs, truth
 from oracle.soft_argmax_ref import RefJointLocationLoss, ref_fwd_bwd, ref_soft_argmax
 
 
@@ -130,3 +130,34 @@ def test_targets_must_not_require_grad():
     gt = torch.zeros(1, 2, 3, requires_grad=True)
     with pytest.raises(AssertionError):
         RefJointLocationLoss()(h, gt, torch.ones(1, 2, 1), torch.ones(1, 1))
+
+
+@pytest.mark.parametrize("name", post_golden_names())
+def test_post_processing_oracle_matches_reference_golden(name):
+    """oracle/coords_post_ref.py against fixtures produced by the reference's own warp_coord_to_original / pixel2cam
+    (common/utils/pose_utils.py:68-75, 14-20): same numpy statements on the same inputs -> bit-identical."""
+    g = load_post_golden(name)
+    coords, flipped, bbox, center, f, c = coords_post_ref.make_inputs(g["B"], g["J"], g["D"], g["H"], g["W"], int(g["seed"]), bool(g["flip"]))
+    assert np.array_equal(coords, g["coords"]) and np.array_equal(bbox, g["bbox"]) and np.array_equal(f, g["f"])
+    merged, pix, cam = coords_post_ref.post_process(coords, flipped, g["pairs"], bbox, center, f, c, g["root"], g["D"], (g["H"], g["W"]),
+                                                    float(g["bbox_3d_depth"]))
+    assert np.array_equal(merged, g["merged"]) and np.array_equal(pix, g["pixel"]) and np.array_equal(cam, g["cam"])
+    if g["root"] >= 0:
+        assert np.abs(cam[:, g["root"]]).max() == 0.0
+
+
+def test_post_processing_known_answers():
+    """Centre voxel of the volume -> centre of the box at the box's depth; on the optical axis -> x = y = 0 in camera space."""
+    D = H = W = 64
+    coords = np.array([[[W / 2, H / 2, D / 2]]], np.float32)
+    bbox = np.array([[100., 50., 200., 300.]], np.float32)
+    center = np.array([[0., 0., 4000.]], np.float32)
+    f = np.array([[1000., 1000.]], np.float32)
+    c = np.array([[200., 200.]], np.float32)
+    _, pix, cam = coords_post_ref.post_process(coords, None, (), bbox, center, f, c, -1, D, (H, W), 2000.0)
+    assert np.allclose(pix[0, 0], [200., 200., 4000.])
+    assert np.allclose(cam[0, 0], [0., 0., 4000.])
+    # flip merge of a pass with itself mirrored back is the identity
+    a = torch.rand(2, 6, 3) * 63
+    b = a.clone(); b[:, :, 0] = W - b[:, :, 0] - 1
+    assert torch.allclose(coords_post_ref.flip_merge(a, b, W, ()), a, atol=1e-5)
