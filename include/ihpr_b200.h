@@ -99,6 +99,34 @@ int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, i
  * ihpr_integral_l1_fwd_bwd into autograd's answer for an arbitrary upstream gradient.  n = B*J*D*H*W elements. */
 int ihpr_scale_grad(void *grad_heat, int dtype, size_t n, const float *grad_out, void *stream);
 
+/* Training-sample preparation of DatasetLoader.__getitem__ (data/dataset.py:84-152) for a whole batch on the device.
+ *
+ * ihpr_augment_patches -- generate_patch_image (dataset.py:201-221: optional horizontal flip, cv2.warpAffine with
+ * INTER_LINEAR and a constant zero border, BGR -> RGB, float32), the colour scale + clip of dataset.py:92-93 and the
+ * ToTensor + Normalize transform of common/base.py:93-95, i.e. out = (clip(patch * color_scale, 0, 255) - mean) / std
+ * (the reference does NOT divide by 255: ToTensor only rescales uint8 input).  The warp restates OpenCV's fixed-point
+ * algorithm for uint8 images: patches are bit-identical to the reference's.
+ *   images (B, Hs, Ws, 3) uint8 BGR as cv2.imread returns them, padded to a common Hs x Ws; sizes (B,2) int32 = valid
+ *   rows, cols of each image; trans (B,6) double = the forward 2x3 patch transform of gen_trans_from_patch_cv
+ *   (dataset.py:229-257) computed for the ALREADY MIRRORED box centre when do_flip[b] != 0; color_scale (B,3) in RGB
+ *   order; pixel_mean / pixel_std: HOST pointers to 3 floats (main/config.py:31-32); out (B,3,out_h,out_w) fp32, or
+ *   (B,out_h,out_w,3) when channels_last != 0.  All other pointers are device pointers.
+ *
+ * ihpr_augment_joints -- dataset.py:96-135,148-149: mirror x and swap left/right joints when flipped (flip_perm: the
+ * pair swaps as one permutation, nullable), trans_point2d, depth / (bbox3d_depth / 2 * scale) -> [0, 1), visibility
+ * *= inside the patch and the depth range, coordinates scaled from the (in_h, in_w) patch to the (out_h, out_w, depth_dim)
+ * heat-map volume.  joint_img (B,J,3) double: x, y in source-image pixels, z root-relative depth (mm); joint_vis (B,J)
+ * double; scale (B) double = the augmentation scale; gt_coord (B,J,3) / gt_vis (B,J) fp32 out, ready for
+ * ihpr_integral_l1_fwd*.  fp64 arithmetic as in the reference's numpy (agreement ~1e-12 before the final fp32 cast). */
+int ihpr_augment_patches(const unsigned char *images, const int *sizes, int B, int Hs, int Ws,
+                         const double *trans, const int *do_flip, const float *color_scale,
+                         const float *pixel_mean, const float *pixel_std,
+                         int out_h, int out_w, float *out, int channels_last, void *stream);
+int ihpr_augment_joints(const double *joint_img, const double *joint_vis, const int *sizes,
+                        const double *trans, const double *scale, const int *do_flip, const int *flip_perm,
+                        int B, int J, int in_h, int in_w, int out_h, int out_w, int depth_dim, double bbox3d_depth,
+                        float *gt_coord, float *gt_vis, void *stream);
+
 /* Test-time post-processing of the (B, J, 3) soft-argmax result in one launch, all buffers on the device:
  *   1. flip-test merge, main/test.py:67-76 -- coords_flipped (nullable = no flip test) is the soft_argmax of the
  *      mirrored image: x' = W - x - 1, joint j takes the flipped pass's joint flip_perm[j] (nullable = identity;

@@ -284,6 +284,46 @@ int ihpr_scale_grad(void* grad_heat, int dtype, size_t n, const float* grad_out,
     return IHPR_OK;
 }
 
+int ihpr_augment_patches(const unsigned char* images, const int* sizes, int B, int Hs, int Ws, const double* trans, const int* do_flip,
+                         const float* color_scale, const float* pixel_mean, const float* pixel_std, int out_h, int out_w, float* out,
+                         int channels_last, void* stream) {
+    g_launches = 0;
+    if (!images || !sizes || !trans || !do_flip || !color_scale || !pixel_mean || !pixel_std || !out) return fail(IHPR_EINVAL, "null argument");
+    if (B < 0 || Hs <= 0 || Ws <= 0 || out_h <= 0 || out_w <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if (Hs > 32767 || Ws > 32767) return fail(IHPR_EINVAL, "source images larger than 32767 pixels are not supported (got %dx%d)", Hs, Ws);
+    if (B > 65535) return fail(IHPR_EINVAL, "at most 65535 samples per call (got %d)", B);
+    for (int c = 0; c < 3; ++c)
+        if (!(pixel_std[c] != 0.f)) return fail(IHPR_EINVAL, "pixel_std[%d] is zero or NaN", c);
+    if (B == 0) return IHPR_OK;
+    int num_sms = 0;
+    int rc = check_device(out, &num_sms);
+    if (rc) return rc;
+    ihpr::launch_patches(images, sizes, B, Hs, Ws, trans, do_flip, color_scale, pixel_mean, pixel_std, out_h, out_w, out, channels_last != 0,
+                         static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+int ihpr_augment_joints(const double* joint_img, const double* joint_vis, const int* sizes, const double* trans, const double* scale,
+                        const int* do_flip, const int* flip_perm, int B, int J, int in_h, int in_w, int out_h, int out_w, int depth_dim,
+                        double bbox3d_depth, float* gt_coord, float* gt_vis, void* stream) {
+    g_launches = 0;
+    if (!joint_img || !joint_vis || !sizes || !trans || !scale || !do_flip || !gt_coord || !gt_vis) return fail(IHPR_EINVAL, "null argument");
+    if (B < 0 || J <= 0 || in_h <= 0 || in_w <= 0 || out_h <= 0 || out_w <= 0 || depth_dim <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if (!(bbox3d_depth > 0)) return fail(IHPR_EINVAL, "bbox3d_depth must be positive");
+    if ((long long)B * J > 0x7fffffffLL) return fail(IHPR_EINVAL, "B*J does not fit in 31 bits");
+    if (B == 0) return IHPR_OK;
+    int num_sms = 0;
+    int rc = check_device(gt_coord, &num_sms);
+    if (rc) return rc;
+    ihpr::launch_joints(joint_img, joint_vis, sizes, trans, scale, do_flip, flip_perm, B, J, in_h, in_w, out_h, out_w, depth_dim, bbox3d_depth, gt_coord,
+                        gt_vis, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_coords_to_camera(const float* coords, const float* coords_flipped, const int* flip_perm, int B, int J, int D, int H, int W, const float* bbox,
                           const float* center_cam, const float* focal, const float* princpt, float bbox3d_depth, int root_idx, float* merged_out,
                           float* pixel_out, float* cam_out, void* stream) {

@@ -316,6 +316,12 @@ Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok
 int fused_split(const Geometry& g, int dtype);
 cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s);
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
+void launch_patches(const unsigned char* images, const int* sizes, int B, int Hs, int Ws, const double* trans, const int* do_flip,
+                    const float* color_scale, const float* mean, const float* stdv, int out_h, int out_w, float* out, int channels_last,
+                    cudaStream_t s);
+void launch_joints(const double* joint_img, const double* joint_vis, const int* sizes, const double* trans, const double* scale, const int* do_flip,
+                   const int* perm, int B, int J, int in_h, int in_w, int out_h, int out_w, int depth_dim, double bbox3d_depth, float* gt_coord,
+                   float* gt_vis, cudaStream_t s);
 void launch_coords_post(const float* coords, const float* flipped, const int* perm, int B, int J, int D, int H, int W, const float* bbox,
                         const float* center, const float* focal, const float* princpt, float bbox3d_depth, int root, float* merged, float* pixel,
                         float* cam, cudaStream_t s);

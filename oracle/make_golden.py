@@ -125,6 +125,76 @@ def make_post_goldens():
         print(f"{name:34s} |cam|max={np.abs(cam).max():.1f} {os.path.getsize(path)/1024:.1f} KiB")
 
 
+# name, image h, w, J, input_shape, output_shape, depth_dim, seeds (one sample each), flip pairs
+AUG_CASES = [
+    ("aug_h36m_like", 500, 520, 18, (256, 256), (64, 64), 64, (31, 32, 33, 34, 35, 36), ((1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13))),
+    ("aug_rect_small", 240, 360, 5, (96, 128), (24, 32), 16, (41, 42, 43, 44), ((0, 1), (1, 2))),
+]
+
+
+def make_aug_goldens():
+    """tests/golden/aug_*.npz by running the reference's own DatasetLoader.__getitem__ (data/dataset.py:48-152, which calls the
+    real cv2.warpAffine / getAffineTransform and torchvision's ToTensor + Normalize as common/base.py:93-95 builds them) on
+    seeded synthetic images written as PNG.  utils/vis.py needs matplotlib (absent): a placeholder module with the two names
+    dataset.py imports is registered first; no reference line is edited.  Pins oracle/augment_ref.py: patches bit-identical."""
+    import hashlib
+    import random
+    import types
+    import cv2
+    import torchvision.transforms as transforms
+    from oracle import augment_ref as ar
+    ref = Reference()
+    vis_stub = types.ModuleType("utils.vis")
+    vis_stub.vis_keypoints = vis_stub.vis_3d_skeleton = lambda *a, **k: None
+    sys.modules.setdefault("utils.vis", vis_stub)
+    import dataset as ref_dataset                                   # /root/reference/data/dataset.py (scratch copy)
+    cfg = ref.cfg
+    for name, h, w, J, in_shape, out_shape, depth_dim, seeds, pairs in AUG_CASES:
+        cfg.input_shape, cfg.output_shape, cfg.depth_dim = in_shape, out_shape, depth_dim
+        depth = float(cfg.bbox_3d_shape[0])
+        tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=cfg.pixel_mean, std=cfg.pixel_std)])
+        out = dict(h=h, w=w, J=J, input_shape=np.array(in_shape), output_shape=np.array(out_shape), depth_dim=depth_dim, seeds=np.array(seeds),
+                   pairs=np.array(pairs, np.int32).reshape(-1, 2), bbox_3d_depth=depth, pixel_mean=np.array(cfg.pixel_mean), pixel_std=np.array(cfg.pixel_std),
+                   cv2_version=str(cv2.__version__))
+        rows = []
+        for seed in seeds:
+            img = ar.synthetic_image(h, w, seed)
+            bbox, joints, vis = ar.synthetic_annotation(h, w, J, seed)
+            path = os.path.join(ref.tmp, "img_%d.png" % seed)
+            cv2.imwrite(path, img)
+
+            class Db:
+                joint_num, skeleton, lr_skeleton, flip_pairs, joints_have_depth = J, (), (), pairs, True
+
+                def load_data(self):
+                    return [dict(img_path=path, bbox=bbox.copy(), joint_img=joints.copy(), joint_vis=vis.copy())]
+
+            loader = ref_dataset.DatasetLoader(Db(), True, tf)
+            np.random.seed(seed); random.seed(seed)
+            aug = ref_dataset.get_aug_config()                      # the draw __getitem__ is about to make
+            np.random.seed(seed); random.seed(seed)
+            assert ar.get_aug_config() == aug, name
+            np.random.seed(seed); random.seed(seed)
+            r_img, r_joint, r_vis, r_hd = loader[0]
+            scale, rot, do_flip, color_scale = aug
+            _, r_trans = ref_dataset.generate_patch_image(img[:1000, :1000], bbox, do_flip, scale, rot)
+            o_img, o_joint, o_vis, o_trans = ar.get_item(img, bbox, joints, vis, pairs, aug, in_shape, out_shape, depth_dim, depth,
+                                                         cfg.pixel_mean, cfg.pixel_std)
+            r_img = r_img.numpy()
+            assert np.abs(o_trans - r_trans).max() <= 1e-9, (name, seed, np.abs(o_trans - r_trans).max())
+            assert np.array_equal(o_img, r_img), (name, seed, np.abs(o_img - r_img).max(), (o_img != r_img).mean())
+            assert np.abs(o_joint - r_joint).max() <= 1e-4 and np.array_equal(o_vis, r_vis), (name, seed)
+            rows.append(dict(aug=np.array([scale, rot, float(do_flip)] + list(color_scale)), trans=r_trans, joint=r_joint, vis=r_vis, hd=r_hd,
+                             img_sha=np.frombuffer(hashlib.sha256(r_img.tobytes()).digest(), np.uint8), img_sub=r_img.reshape(-1)[::97].copy(),
+                             src_sha=np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8)))
+            print(f"{name:16s} seed {seed}: scale {scale:.3f} rot {rot:6.2f} flip {int(do_flip)}  vis {int(r_vis.sum())}/{J}")
+        for k in rows[0]:
+            out[k] = np.stack([r[k] for r in rows])
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name:34s} {os.path.getsize(path)/1024:.1f} KiB")
+
+
 def dump_reference_state_keys():
     """state_dict keys + shapes of the reference's own get_pose_net (main/model.py:105-114) for ResNet-50 / J=18,
     as a fixture for the checkpoint-compatibility test of ihpr_b200.model (the reference's resnet.py imports
@@ -152,7 +222,11 @@ if __name__ == "__main__":
     if "--post" in sys.argv:                 # only the post-processing fixtures
         make_post_goldens()
         sys.exit(0)
+    if "--aug" in sys.argv:                  # only the augmentation fixtures
+        make_aug_goldens()
+        sys.exit(0)
     if "--keys" not in sys.argv:
         main()
         make_post_goldens()
+        make_aug_goldens()
     dump_reference_state_keys()

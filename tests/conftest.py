@@ -17,12 +17,27 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith("post_"))
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("post_", "aug_")))
 
 
 def post_golden_names():
     """Fixtures of the test-time post-processing (K6), written by `python -m oracle.make_golden --post`."""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "post_*.npz")))
+
+
+def aug_golden_names():
+    """Fixtures of the sample preparation (K7 / K8), written by `python -m oracle.make_golden --aug` from the reference's own
+    DatasetLoader.__getitem__."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "aug_*.npz")))
+
+
+def load_aug_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["pairs"] = tuple((int(a), int(b)) for a, b in g["pairs"])
+    for k in ("h", "w", "J", "depth_dim"):
+        g[k] = int(g[k])
+    g["augs"] = [(float(a[0]), float(a[1]), bool(a[2]), [float(a[3]), float(a[4]), float(a[5])]) for a in g["aug"]]
+    return g
 
 
 def load_post_golden(name):

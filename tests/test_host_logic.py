@@ -1,6 +1,7 @@
 """CPU: host-side mirror of the reference interface -- names, argument checks, error behaviour."""
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -96,3 +97,43 @@ def test_stage_targets_views(built_lib):
     c2, v2, h2 = stage_targets(coord, vis, hd, torch.device("cpu"))
     assert torch.equal(c2, coord) and torch.equal(v2, vis) and torch.equal(h2, hd)
     assert c2.data_ptr() + coord.numel() * 4 == v2.data_ptr()       # one buffer, back to back
+
+
+def test_aug_config_and_patch_transform_match_reference_fixtures(built_lib):
+    """data.get_aug_config draws what the reference's get_aug_config (dataset.py:184-199) drew under the same seeds, and
+    data.gen_trans_from_patch reproduces the transform cv2.getAffineTransform gave the reference (fixtures: oracle/make_golden.py --aug)."""
+    import random
+    from conftest import aug_golden_names, load_aug_golden
+    from ihpr_b200 import data
+    from oracle import augment_ref as ar
+    for name in aug_golden_names():
+        g = load_aug_golden(name)
+        for n, seed in enumerate(g["seeds"]):
+            np.random.seed(int(seed)); random.seed(int(seed))
+            scale, rot, do_flip, color = data.get_aug_config()
+            assert (scale, float(rot), do_flip, color) == g["augs"][n]
+            bbox, _, _ = ar.synthetic_annotation(g["h"], g["w"], g["J"], int(seed))
+            t = data.patch_params(bbox, g["w"], g["augs"][n], tuple(g["input_shape"]))
+            assert np.abs(t - g["trans"][n]).max() <= 1e-9
+    # inverse map: gen_trans(inv=True) undoes gen_trans
+    a = data.gen_trans_from_patch(120.5, 80.25, 200., 150., 256, 256, 1.1, 25., inv=False)
+    b = data.gen_trans_from_patch(120.5, 80.25, 200., 150., 256, 256, 1.1, 25., inv=True)
+    full = lambda m: np.vstack([m, [0, 0, 1]])          # noqa: E731
+    assert np.abs(full(a) @ full(b) - np.eye(3)).max() <= 1e-5
+
+
+def test_aug_record_layout_is_aligned(built_lib):
+    from ihpr_b200 import data
+    for B, J in ((1, 1), (3, 17), (32, 18), (5, 2)):
+        layout, nbytes = data._record_layout(B, J)
+        ends = 0
+        for name, (off, dt, n) in layout.items():
+            assert off % np.dtype(dt).itemsize == 0 and off >= ends
+            ends = off + n * np.dtype(dt).itemsize
+        assert ends == nbytes
+
+
+def test_augment_batch_has_no_cpu_path(built_lib):
+    import ihpr_b200
+    with pytest.raises(ihpr_b200.IhprError):
+        ihpr_b200.augment_batch(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), [[8, 8]], [[0, 0, 8, 8]], np.zeros((1, 2, 3)), np.ones((1, 2)), [ihpr_b200.data.NO_AUG])

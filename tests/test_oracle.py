@@ -161,3 +161,23 @@ def test_post_processing_known_answers():
     a = torch.rand(2, 6, 3) * 63
     b = a.clone(); b[:, :, 0] = W - b[:, :, 0] - 1
     assert torch.allclose(coords_post_ref.flip_merge(a, b, W, ()), a, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", __import__("conftest").aug_golden_names())
+def test_augment_oracle_matches_reference_golden(name):
+    """oracle/augment_ref.py (numpy restatement incl. OpenCV's fixed-point warpAffine) against what the reference's own
+    DatasetLoader.__getitem__ returned: normalised patch bit-identical (sha256 of the fp32 bytes), joints to 1e-6."""
+    import hashlib
+    from conftest import load_aug_golden
+    from oracle import augment_ref as ar
+    g = load_aug_golden(name)
+    for n, seed in enumerate(g["seeds"]):
+        img = ar.synthetic_image(g["h"], g["w"], int(seed))
+        assert np.array_equal(np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8), g["src_sha"][n])
+        bbox, joints, vis = ar.synthetic_annotation(g["h"], g["w"], g["J"], int(seed))
+        o_img, o_joint, o_vis, o_trans = ar.get_item(img, bbox, joints, vis, g["pairs"], g["augs"][n], tuple(g["input_shape"]), tuple(g["output_shape"]),
+                                                     g["depth_dim"], float(g["bbox_3d_depth"]), g["pixel_mean"], g["pixel_std"])
+        assert np.array_equal(np.frombuffer(hashlib.sha256(o_img.tobytes()).digest(), np.uint8), g["img_sha"][n])
+        assert np.array_equal(o_img.reshape(-1)[::97], g["img_sub"][n])
+        assert np.abs(o_trans - g["trans"][n]).max() <= 1e-9
+        assert np.abs(o_joint - g["joint"][n]).max() <= 1e-4 and np.array_equal(o_vis, g["vis"][n])
