@@ -339,6 +339,11 @@ def run_b200(args):
                "sample": "B=%d of the B=%d batch (J=%d, %dx%dx%d fp32), %d fwd+bwd iterations in %.1f s, torch CPU eager ops "
                          "(oracle/soft_argmax_ref.py = reference loss.py:13-52 op for op), host has %d logical CPUs"
                          % (sB, B, J, D, H, W, n, dt, os.cpu_count())}
+        # the reference's own CPU-runnable case (B=1) on ONE thread, reported next to the all-cores figure
+        torch.set_num_threads(1)
+        v1, _, n1, dt1 = cpu_reference_leg(1, J, D, H, W, min_seconds=4.0, warmup=1)
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": "B=1 (BASELINE configs[0]), %d iterations in %.1f s" % (n1, dt1)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
