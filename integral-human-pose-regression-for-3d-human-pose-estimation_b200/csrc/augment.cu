@@ -46,8 +46,11 @@ constexpr int kAbBits = 10, kInterBits = 5;
 
 __global__ void __launch_bounds__(256) patch_kernel(PatchParams p) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
+    __shared__ InvMap inv;                                   // one inversion (a double division) per block, not per pixel
+    if (threadIdx.x == 0 && threadIdx.y == 0) inv = invert_affine(p.trans + (size_t)b * 6);
+    __syncthreads();
     if (x >= p.out_w || y >= p.out_h) return;
-    const InvMap im = invert_affine(p.trans + (size_t)b * 6);
+    const InvMap im = inv;
     const double ab = (double)(1 << kAbBits);
     const int round_delta = (1 << kAbBits) / (1 << kInterBits) / 2;
     const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(im.a00, (double)x), ab));

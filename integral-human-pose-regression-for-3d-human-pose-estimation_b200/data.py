@@ -34,37 +34,55 @@ def get_aug_config(scale_factor=0.25, rot_factor=30, color_factor=0.2):
 NO_AUG = (1.0, 0, False, [1.0, 1.0, 1.0])     # dataset.py:88 (test-time / do_augment False)
 
 
-def gen_trans_from_patch(c_x, c_y, src_width, src_height, dst_width, dst_height, scale, rot, inv=False):
-    """dataset.py:229-257: the affine map taking the (scaled, rotated) box around (c_x, c_y) onto the dst_width x dst_height
-    patch, as a 2x3 float64 matrix.  The reference builds three float32 point pairs (centre, centre + down, centre + right)
-    and lets cv2.getAffineTransform solve for the map; with those pairs the solution is  L = D S^-1,  t = dc - L sc  where
-    the columns of S / D are the (down, right) edge vectors."""
-    f32 = np.float32
+def gen_trans_batch(c_x, c_y, src_width, src_height, dst_width, dst_height, scale, rot, inv=False):
+    """dataset.py:229-257 for n boxes at once: (n, 2, 3) float64.  The reference builds three float32 point pairs per box (centre,
+    centre + down, centre + right; the edge vectors rotated in double, rounded to float32) and lets cv2.getAffineTransform solve
+    for the map; with those pairs the solution is  L = D S^-1,  t = dc - L sc  where the columns of S / D are the (down, right)
+    edge vectors.  The float32 roundings are kept where the reference has them."""
+    f32, f64 = np.float32, np.float64
+    c_x, c_y, src_width, src_height, scale, rot = (np.atleast_1d(np.asarray(v, f64)) for v in (c_x, c_y, src_width, src_height, scale, rot))
     rad = np.pi * rot / 180
     sn, cs = np.sin(rad), np.cos(rad)
-    half_h, half_w = f32(src_height * scale * 0.5), f32(src_width * scale * 0.5)
-    down = np.array([f32(0) * cs - half_h * sn, f32(0) * sn + half_h * cs], dtype=f32)          # rotate_2d((0, h/2))
-    right = np.array([half_w * cs - f32(0) * sn, half_w * sn + f32(0) * cs], dtype=f32)         # rotate_2d((w/2, 0))
-    sc = np.array([c_x, c_y], dtype=f32)
-    dc = np.array([dst_width * 0.5, dst_height * 0.5], dtype=f32)
-    src = np.stack([sc, sc + down, sc + right]).astype(np.float64)
-    dst = np.stack([dc, dc + np.array([0, dst_height * 0.5], f32), dc + np.array([dst_width * 0.5, 0], f32)]).astype(np.float64)
+    half_h = (src_height * scale * 0.5).astype(f32).astype(f64)
+    half_w = (src_width * scale * 0.5).astype(f32).astype(f64)
+    down = np.stack([-(half_h * sn), half_h * cs], 1).astype(f32)                 # rotate_2d((0, h/2))
+    right = np.stack([half_w * cs, half_w * sn], 1).astype(f32)                  # rotate_2d((w/2, 0))
+    sc = np.stack([c_x, c_y], 1).astype(f32)
+    n = sc.shape[0]
+    dc = np.broadcast_to(np.array([dst_width * 0.5, dst_height * 0.5], f32), (n, 2))
+    src = np.stack([sc, sc + down, sc + right], 1).astype(f64)                  # (n, 3 points, 2), sums in float32
+    dst = np.stack([dc, dc + np.array([0, dst_height * 0.5], f32), dc + np.array([dst_width * 0.5, 0], f32)], 1).astype(f64)
     if inv:
         src, dst = dst, src
-    S = np.stack([src[1] - src[0], src[2] - src[0]], axis=1)
-    D = np.stack([dst[1] - dst[0], dst[2] - dst[0]], axis=1)
-    L = D @ np.linalg.inv(S)
-    return np.concatenate([L, (dst[0] - L @ src[0])[:, None]], axis=1)
+    S = np.stack([src[:, 1] - src[:, 0], src[:, 2] - src[:, 0]], 2)            # (n, 2, 2), columns = edge vectors
+    D = np.stack([dst[:, 1] - dst[:, 0], dst[:, 2] - dst[:, 0]], 2)
+    det = S[:, 0, 0] * S[:, 1, 1] - S[:, 0, 1] * S[:, 1, 0]
+    Sinv = np.stack([np.stack([S[:, 1, 1], -S[:, 0, 1]], 1), np.stack([-S[:, 1, 0], S[:, 0, 0]], 1)], 1) / det[:, None, None]
+    L = D @ Sinv
+    t = dst[:, 0] - np.einsum("nij,nj->ni", L, src[:, 0])
+    return np.concatenate([L, t[:, :, None]], 2)
+
+
+def gen_trans_from_patch(c_x, c_y, src_width, src_height, dst_width, dst_height, scale, rot, inv=False):
+    """dataset.py:229-257 (same argument list): the affine map taking the (scaled, rotated) box around (c_x, c_y) onto the
+    dst_width x dst_height patch, as a 2x3 float64 matrix."""
+    return gen_trans_batch(c_x, c_y, src_width, src_height, dst_width, dst_height, scale, rot, inv)[0]
+
+
+def patch_params_batch(bboxes, img_widths, augs, input_shape):
+    """Forward patch transforms (n, 2, 3) for the (mirrored, when flipped) box centres of dataset.py:204-213.  The centre is computed
+    in the boxes' own dtype, as the reference's  float(bbox[0] + 0.5 * bbox[2])  does, then carried in double."""
+    bboxes = np.asarray(bboxes)
+    c_x = (bboxes[:, 0] + 0.5 * bboxes[:, 2]).astype(np.float64)
+    c_y = (bboxes[:, 1] + 0.5 * bboxes[:, 3]).astype(np.float64)
+    flip = np.array([bool(a[2]) for a in augs])
+    c_x = np.where(flip, np.asarray(img_widths, np.float64) - c_x - 1, c_x)
+    return gen_trans_batch(c_x, c_y, bboxes[:, 2], bboxes[:, 3], input_shape[1], input_shape[0], [a[0] for a in augs], [a[1] for a in augs])
 
 
 def patch_params(bbox, img_width, aug, input_shape):
-    """Per-sample launch parameters: the forward patch transform for the (mirrored, when flipped) box centre of
-    dataset.py:204-213."""
-    scale, rot, do_flip, _ = aug
-    c_x, c_y = float(bbox[0] + 0.5 * bbox[2]), float(bbox[1] + 0.5 * bbox[3])
-    if do_flip:
-        c_x = img_width - c_x - 1
-    return gen_trans_from_patch(c_x, c_y, float(bbox[2]), float(bbox[3]), input_shape[1], input_shape[0], scale, rot)
+    """One sample of ``patch_params_batch``."""
+    return patch_params_batch(np.asarray(bbox)[None], [img_width], [aug], input_shape)[0]
 
 
 def _record_layout(B, J):
@@ -119,9 +137,8 @@ def augment_batch(images, sizes, bboxes, joint_img, joint_vis, augs, flip_pairs=
         off, dt, n = layout[name]
         return raw[off:off + n * np.dtype(dt).itemsize].view(dt)
 
-    trans = field("trans").reshape(B, 6)
-    for b in range(B):
-        trans[b] = patch_params(bboxes[b], int(sizes[b, 1]), augs[b], (in_h, in_w)).reshape(6)
+    if B:
+        field("trans")[:] = patch_params_batch(bboxes, sizes[:, 1], augs, (in_h, in_w)).reshape(-1)
     field("scale")[:] = [a[0] for a in augs]
     field("joint_img")[:] = joint_img.reshape(-1)
     field("joint_vis")[:] = joint_vis.reshape(-1)
