@@ -118,10 +118,13 @@ class _IntegralL1(torch.autograd.Function):
         ctx.joint_num = J
         ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
         ctx.mark_non_differentiable(coords)
+        ctx.set_materialize_grads(False)         # no zero-fill launch for the unused gradient of `coords`
         return loss, coords
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_coords):
+        if grad_loss is None:
+            return None, None, None, None
         heat, coords, stats, gt, vis, hd = ctx.saved_tensors
         J = ctx.joint_num
         B, D, H, W = _shape(heat, J)
@@ -160,10 +163,13 @@ class _IntegralL1Fused(torch.autograd.Function):
         ctx.grad_unit = grad_unit           # consumed (scaled in place) by the first backward
         ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
         ctx.mark_non_differentiable(coords)
+        ctx.set_materialize_grads(False)         # no zero-fill launch for the unused gradient of `coords`
         return loss, coords
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_coords):
+        if grad_loss is None:
+            return None, None, None, None
         grad_heat = ctx.grad_unit
         go = grad_loss if grad_loss.dtype == torch.float32 else grad_loss.to(torch.float32)
         L = lib()
@@ -322,10 +328,13 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         ctx.save_for_backward(xb, wb, bf, coords, stats, gt, vis, hd)
         ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape))
         ctx.mark_non_differentiable(coords)
+        ctx.set_materialize_grads(False)
         return loss, coords
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_coords):
+        if grad_loss is None:
+            return None, None, None, None, None, None
         xb, wb, bf, coords, stats, gt, vis, hd = ctx.saved_tensors
         x_dtype, w_dtype, b_dtype, w_shape = ctx.meta
         B, K, H, W = xb.shape
