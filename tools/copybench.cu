@@ -20,7 +20,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t par) {
 
 constexpr int NCW = 16;      // consumer warps
 
-template <int CHUNK, int STAGES, int MODE>
+template <int CHUNK, int STAGES, int MODE, int ILV>
 __global__ void __launch_bounds__(32 * (NCW + 2), 1) copy_ring_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ outp, size_t nchunks) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * CHUNK);
@@ -36,11 +36,13 @@ __global__ void __launch_bounds__(32 * (NCW + 2), 1) copy_ring_kernel(const uint
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const size_t lo = nchunks * blockIdx.x / gridDim.x, hi = nchunks * (blockIdx.x + 1) / gridDim.x;
+    // ILV 0: each CTA streams one contiguous range; ILV 1: chunks dealt round-robin (chunk = first + it * step)
+    const size_t lo = ILV ? blockIdx.x : nchunks * blockIdx.x / gridDim.x, hi = ILV ? nchunks : nchunks * (blockIdx.x + 1) / gridDim.x;
+    const size_t step = ILV ? gridDim.x : 1;
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (size_t c = lo; c < hi; ++c, ++it) {
+            for (size_t c = lo; c < hi; c += step, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(empty + s, ph ^ 1);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(full + s)), "r"(CHUNK) : "memory");
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(32 * (NCW + 2), 1) copy_ring_kernel(const uint
     } else if (warp == 1) {
         if (MODE != 2 && lane == 0) {      // the store thread
             uint32_t it = 0;
-            for (size_t c = lo; c < hi; ++c, ++it) {
+            for (size_t c = lo; c < hi; c += step, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(MODE == 0 ? full + s : done + s, ph);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(outp + c * CHUNK), "r"(s32(smem + (size_t)s * CHUNK)), "r"(CHUNK)
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(32 * (NCW + 2), 1) copy_ring_kernel(const uint
     } else if (MODE != 0) {
         const int cw = warp - 2;
         uint32_t it = 0;
-        for (size_t c = lo; c < hi; ++c, ++it) {
+        for (size_t c = lo; c < hi; c += step, ++it) {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(full + s, ph);
             float4* st = reinterpret_cast<float4*>(smem + (size_t)s * CHUNK);
@@ -91,10 +93,10 @@ __global__ void __launch_bounds__(32 * (NCW + 2), 1) copy_ring_kernel(const uint
     }
 }
 
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, int ILV>
 int run(const uint8_t* a, uint8_t* b, size_t bytes, int sms, const char* name) {
     constexpr int CH = 32768;
-    auto k = copy_ring_kernel<CH, STAGES, MODE>;
+    auto k = copy_ring_kernel<CH, STAGES, MODE, ILV>;
     const int smem = STAGES * CH + 3 * STAGES * 8;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1;
@@ -108,7 +110,7 @@ int run(const uint8_t* a, uint8_t* b, size_t bytes, int sms, const char* name) {
         if (ms < best) best = ms;
     }
     CK(cudaGetLastError());
-    printf("%-58s %d stages: %7.1f us  %7.1f GB/s (r+w)\n", name, STAGES, best * 1e3, 2.0 * bytes / best / 1e6);
+    printf("%-58s %s %d stages: %7.1f us  %7.1f GB/s (r+w)\n", name, ILV ? "round-robin chunks" : "contiguous ranges ", STAGES, best * 1e3, 2.0 * bytes / best / 1e6);
     return 0;
 }
 
@@ -118,12 +120,14 @@ int main() {
     CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b, bytes));
     CK(cudaMemset(a, 1, bytes)); CK(cudaMemset(b, 2, bytes));
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    if (run<0, 6>(a, b, bytes, sms, "mode 0  TMA load -> TMA store (pure DMA)")) return 1;
-    if (run<1, 6>(a, b, bytes, sms, "mode 1  TMA load -> LDS/STS in place -> TMA store")) return 1;
-    if (run<2, 6>(a, b, bytes, sms, "mode 2  TMA load -> LDS -> STG.128")) return 1;
-    if (run<0, 4>(a, b, bytes, sms, "mode 0  TMA load -> TMA store (pure DMA)")) return 1;
-    if (run<1, 4>(a, b, bytes, sms, "mode 1  TMA load -> LDS/STS in place -> TMA store")) return 1;
-    if (run<2, 4>(a, b, bytes, sms, "mode 2  TMA load -> LDS -> STG.128")) return 1;
+    if (run<0, 6, 0>(a, b, bytes, sms, "mode 0  TMA load -> TMA store (pure DMA)")) return 1;
+    if (run<1, 6, 0>(a, b, bytes, sms, "mode 1  TMA load -> LDS/STS in place -> TMA store")) return 1;
+    if (run<2, 6, 0>(a, b, bytes, sms, "mode 2  TMA load -> LDS -> STG.128")) return 1;
+    if (run<0, 6, 1>(a, b, bytes, sms, "mode 0  TMA load -> TMA store (pure DMA)")) return 1;
+    if (run<1, 6, 1>(a, b, bytes, sms, "mode 1  TMA load -> LDS/STS in place -> TMA store")) return 1;
+    if (run<2, 6, 1>(a, b, bytes, sms, "mode 2  TMA load -> LDS -> STG.128")) return 1;
+    if (run<0, 4, 0>(a, b, bytes, sms, "mode 0  TMA load -> TMA store (pure DMA)")) return 1;
+    if (run<2, 4, 1>(a, b, bytes, sms, "mode 2  TMA load -> LDS -> STG.128")) return 1;
     // check mode 1 really transformed the data
     float h[4]; CK(cudaMemcpy(h, b, 16, cudaMemcpyDeviceToHost));
     printf("sample out %g\n", h[0]);
