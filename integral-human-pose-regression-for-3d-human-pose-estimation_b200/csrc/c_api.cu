@@ -252,7 +252,11 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.grad_heat = grad_heat;
     p.S = S;
     p.loss_scale = scale;
-    p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;
+#ifdef IHPR_TIMING_EXPERIMENTS
+    p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;      // wrong results: only in builds made for timing experiments
+#else
+    p.debug_no_exchange = 0;
+#endif
     const cudaError_t le = ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream));
     if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
         // the S CTAs of a joint-volume cannot be made co-resident right now (GPU shared with other work): same result

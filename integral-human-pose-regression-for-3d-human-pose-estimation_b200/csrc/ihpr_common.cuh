@@ -302,7 +302,7 @@ struct FusedParams {
     int* epoch;             // launch counter in the workspace; tag = epoch + 1
     int S;                  // CTAs per joint-volume
     float loss_scale;       // 1 / (3 * B * J)
-    int debug_no_exchange;  // timing experiments only (IHPR_DEBUG_NOXCHG=1): skip the cross-CTA trade, WRONG results
+    int debug_no_exchange;  // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_DEBUG_NOXCHG=1): skip the cross-CTA trade, WRONG results
 };
 
 // chunk range of persistent CTA `cta` of G: [cta*Gt/G, (cta+1)*Gt/G)
