@@ -206,6 +206,11 @@ def _normalise(heat):
 def soft_argmax(heatmaps, joint_num):
     """(B, J*D, H, W) heatmaps -> (B, J, 3) expected (x, y, z) voxel coordinates, fp32.
     Same contract as /root/reference/common/nets/loss.py:13-34; D is inferred as C // joint_num."""
+    if isinstance(heatmaps, DeferredHeatmap):
+        d = heatmaps
+        if torch.is_grad_enabled() and d.requires_grad:           # K3 is forward-only: the differentiable route is conv + K1
+            return soft_argmax(d.materialize(), joint_num)
+        return fused_head_soft_argmax(d.feat, d.weight, d.bias, joint_num)
     assert isinstance(heatmaps, torch.Tensor)                    # loss.py:14
     _require_cuda(heatmaps, "heatmaps")
     _shape(heatmaps, joint_num)
@@ -220,6 +225,9 @@ def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords
     fused_backward=True (default when the heatmaps require grad; IHPR_FUSED=0 disables): the forward launch also
     produces d loss / d heat (K5, DRAM traffic 2V) and backward() only applies the upstream gradient.
     fused_backward=False: one forward launch (K1) and one recomputing backward launch (K2), traffic 3V."""
+    if isinstance(heatmap_out, DeferredHeatmap):
+        d = heatmap_out
+        return fused_head_integral_l1_loss(d.feat, d.weight, d.bias, gt_coord, gt_vis, gt_have_depth, return_coords=return_coords)
     _require_cuda(heatmap_out, "heatmap_out")
     if gt_coord.dim() != 3 or gt_coord.shape[2] != 3:
         raise ValueError("gt_coord must be (B, J, 3), got %s" % (tuple(gt_coord.shape),))
@@ -361,7 +369,15 @@ def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth
     """JointLocationLoss(final_layer(x), ...) for training without ever storing the (B, J*D, H, W) heat-map:
     main/model.py:42 + main/train.py:67-71 as two tensor-core launches (K3, K4) plus library GEMMs for dW / dX."""
     _require_cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be (B, K, H, W), got %s" % (tuple(x.shape),))
+    if gt_coord.dim() != 3 or gt_coord.shape[2] != 3:
+        raise ValueError("gt_coord must be (B, J, 3), got %s" % (tuple(gt_coord.shape),))
     B, J = gt_coord.shape[0], gt_coord.shape[1]
+    if x.shape[0] != B:
+        raise ValueError("batch mismatch: features %d vs gt_coord %d" % (x.shape[0], B))
+    if J <= 0 or weight.shape[0] % J != 0:
+        raise ValueError("%d output channels are not a multiple of the %d joints in gt_coord" % (weight.shape[0], J))
     dev = x.device
     gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
     vis = _f32(gt_vis, dev, (B, J), "gt_vis")
@@ -370,6 +386,45 @@ def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth
         bias = torch.zeros(weight.shape[0], device=dev)
     loss, coords = _FusedHeadIntegralL1.apply(x, weight, bias, gt, vis, hd)
     return (loss, coords) if return_coords else loss
+
+
+class DeferredHeatmap:
+    """The output of ``HeadNet.final_layer`` (main/model.py:42) that has NOT been computed: the deconv features plus the 1x1
+    conv's parameters.  ``ResPoseNet(fused_head=True, deferred=True)(img)`` returns one, and the drop-in ``soft_argmax`` /
+    ``JointLocationLoss`` consume it with the fused tensor-core kernels (K3 / K4), so the reference's own call sequences
+
+        heatmap_out = model(input_img); loss = JointLocationLoss(heatmap_out, joint_img, joint_vis, have_depth)   # train.py:64-67
+        heatmap_out = model(input_img); coord_out = soft_argmax(heatmap_out, joint_num)                           # test.py:62-65
+
+    run unchanged while the (B, J*D, H, W) volume never exists.  It answers the shape questions a caller may ask
+    (``shape``, ``size()``, ``dim()``, ``device``, ``dtype``); anything else needs ``materialize()`` (a plain conv)."""
+
+    def __init__(self, feat, weight, bias, joint_num):
+        if feat.dim() != 4:
+            raise ValueError("features must be (B, K, H, W), got %s" % (tuple(feat.shape),))
+        if weight.shape[1] != feat.shape[1]:
+            raise ValueError("weight has %d input channels, features have %d" % (weight.shape[1], feat.shape[1]))
+        self.feat, self.weight, self.bias, self.joint_num = feat, weight, bias, int(joint_num)
+
+    @property
+    def shape(self):
+        return torch.Size((self.feat.shape[0], self.weight.shape[0], self.feat.shape[2], self.feat.shape[3]))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 4
+
+    device = property(lambda self: self.feat.device)
+    dtype = property(lambda self: self.feat.dtype)
+    is_cuda = property(lambda self: self.feat.is_cuda)
+    requires_grad = property(lambda self: self.feat.requires_grad or self.weight.requires_grad)
+
+    def materialize(self):
+        """The heat-map itself, for callers that really need the tensor (differentiable, stock conv)."""
+        w = self.weight.reshape(self.weight.shape[0], self.weight.shape[1], 1, 1)
+        return torch.nn.functional.conv2d(self.feat, w.to(self.feat.dtype), None if self.bias is None else self.bias.to(self.feat.dtype))
 
 
 def flip_perm(joint_num, flip_pairs):

@@ -14,7 +14,7 @@ import sys
 import torch
 import torch.nn as nn
 
-from ..functional import integral_l1_loss
+from ..functional import DeferredHeatmap, integral_l1_loss
 from ..functional import soft_argmax as _soft_argmax
 
 
@@ -36,7 +36,7 @@ def _check_cfg(heatmaps, joint_num):
 
 
 def soft_argmax(heatmaps, joint_num):
-    assert isinstance(heatmaps, torch.Tensor)                            # loss.py:14
+    assert isinstance(heatmaps, (torch.Tensor, DeferredHeatmap))         # loss.py:14
     _check_cfg(heatmaps, joint_num)
     return _soft_argmax(heatmaps, joint_num)
 

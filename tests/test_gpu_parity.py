@@ -407,6 +407,54 @@ def test_fused_head_training_step(case, dev):
         assert err <= 2e-2, (name, err)
 
 
+def test_deferred_heatmap_runs_the_reference_call_sequences(dev):
+    """with ResPoseNet(fused_head=True, deferred=True) the reference's own two-call sequences -- train.py:64-71
+    (model -> JointLocationLoss -> backward) and test.py:62-65 (model -> soft_argmax) -- reach K3 / K4 unchanged."""
+    import types
+    import ihpr_b200
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.nets.loss import JointLocationLoss, soft_argmax
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=32, input_shape=(128, 128), output_shape=(32, 32))
+    J = 4
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, J, fused_head=True, deferred=True).to(dev)
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.05)
+    x = torch.randn(2, 3, 128, 128, device=dev)
+    gt = torch.rand(2, J, 3, device=dev) * torch.tensor([32, 32, 32], device=dev)
+    vis, hd = torch.ones(2, J, 1, device=dev), torch.ones(2, 1, device=dev)
+    crit = JointLocationLoss()
+    # train.py:64-71
+    heatmap_out = net(x)
+    assert isinstance(heatmap_out, ihpr_b200.DeferredHeatmap) and heatmap_out.shape == (2, J * 32, 32, 32)
+    loss = crit(heatmap_out, gt, vis, hd)
+    loss.backward()
+    g_fused = net.head.final_layer.weight.grad.clone()
+    g_back = net.backbone.conv1.weight.grad.clone()
+    net.zero_grad()
+    net.deferred = False                                    # the same parameters through the stored heat-map (conv + K5)
+    loss_ref = crit(net(x), gt, vis, hd)
+    loss_ref.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 5e-3 * max(1.0, abs(loss_ref.item()))         # bf16 operands in K3 / K4
+    gw = net.head.final_layer.weight.grad
+    assert (g_fused - gw).abs().max().item() <= 3e-2 * gw.abs().max().item()
+    gb = net.backbone.conv1.weight.grad
+    assert (g_back - gb).abs().max().item() <= 5e-2 * gb.abs().max().item()
+    # test.py:62-65
+    net.deferred = True
+    net.eval()
+    with torch.no_grad():
+        coord_out = soft_argmax(net(x), J)
+        assert torch.equal(coord_out, net.predict(x))
+        net.deferred = False
+        coord_ref = soft_argmax(net(x), J)
+    assert (coord_out - coord_ref).abs().max().item() <= 0.05
+    # with grad enabled soft_argmax on a deferred heat-map stays differentiable (conv + K1)
+    net.deferred = True
+    c = soft_argmax(net(x), J)
+    c.sum().backward()
+    assert net.head.final_layer.weight.grad is not None
+
+
 def test_empty_batch_and_large_batch(dev):
     """edge sizes: an empty batch behaves like the reference (empty coords, NaN mean); a 2.25 GiB batch (B=72, J=18, 64^3 fp32 --
     joint-volume offsets beyond 2^31 bytes) keeps the invariants."""

@@ -137,3 +137,21 @@ def test_augment_batch_has_no_cpu_path(built_lib):
     import ihpr_b200
     with pytest.raises(ihpr_b200.IhprError):
         ihpr_b200.augment_batch(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), [[8, 8]], [[0, 0, 8, 8]], np.zeros((1, 2, 3)), np.ones((1, 2)), [ihpr_b200.data.NO_AUG])
+
+
+def test_deferred_heatmap_answers_shape_questions(built_lib):
+    """The stand-in for final_layer's output behaves like the (B, J*D, H, W) tensor for shape queries and
+    materialises to exactly the conv it stands for."""
+    import ihpr_b200
+    from ihpr_b200.nets import loss
+    torch.manual_seed(0)
+    feat, w, b = torch.randn(2, 8, 4, 6), torch.randn(12, 8, 1, 1), torch.randn(12)
+    d = ihpr_b200.DeferredHeatmap(feat, w, b, 3)
+    assert d.shape == (2, 12, 4, 6) and d.size() == d.shape and d.size(1) == 12 and d.dim() == 4
+    assert d.device == feat.device and d.dtype == feat.dtype and not d.is_cuda and not d.requires_grad
+    assert torch.equal(d.materialize(), torch.nn.functional.conv2d(feat, w, b))
+    loss._check_cfg(d, 3)                                   # no cfg loaded: passes
+    with pytest.raises(ValueError, match="input channels"):
+        ihpr_b200.DeferredHeatmap(feat, torch.randn(12, 7, 1, 1), b, 3)
+    with pytest.raises(ihpr_b200.IhprError):                # consuming it needs the CUDA path
+        loss.soft_argmax(d, 3)
