@@ -99,6 +99,12 @@ int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, i
  * ihpr_integral_l1_fwd_bwd into autograd's answer for an arbitrary upstream gradient.  n = B*J*D*H*W elements. */
 int ihpr_scale_grad(void *grad_heat, int dtype, size_t n, const float *grad_out, void *stream);
 
+/* JointLocationLoss.forward (common/nets/loss.py:49-52) on coordinates that already exist -- the companion of
+ * ihpr_head_softargmax_fwd, which produces coords without a heat-map:
+ *   loss = mean_{b,j} (|dx| + |dy| + |dz| * have_depth[b]) * vis[b,j] / 3.   One launch, fixed summation order. */
+int ihpr_integral_l1_from_coords(const float *coords, const float *gt, const float *vis, const float *have_depth,
+                                 int B, int J, float *loss, void *stream);
+
 /* Training-sample preparation of DatasetLoader.__getitem__ (data/dataset.py:84-152) for a whole batch on the device.
  *
  * ihpr_augment_patches -- generate_patch_image (dataset.py:201-221: optional horizontal flip, cv2.warpAffine with

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ihpr_scale_grad": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "ihpr_augment_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 5 + [c_int, c_int, c_void_p, c_int, c_void_p]),
     "ihpr_augment_joints": (c_int, [c_void_p] * 7 + [c_int] * 7 + [ctypes.c_double] + [c_void_p] * 3),
+    "ihpr_integral_l1_from_coords": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p]),
     "ihpr_coords_to_camera": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 4),
     "ihpr_head_softargmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p, c_void_p, c_void_p]),
     "ihpr_head_integral_l1_bwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p] * 9),

@@ -328,6 +328,21 @@ int ihpr_augment_joints(const double* joint_img, const double* joint_vis, const 
     return IHPR_OK;
 }
 
+int ihpr_integral_l1_from_coords(const float* coords, const float* gt, const float* vis, const float* have_depth, int B, int J, float* loss,
+                                 void* stream) {
+    g_launches = 0;
+    if (!coords || !gt || !vis || !have_depth || !loss) return fail(IHPR_EINVAL, "null argument");
+    if (B <= 0 || J <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if ((long long)B * J > 0x7fffffffLL) return fail(IHPR_EINVAL, "B*J does not fit in 31 bits");
+    int num_sms = 0;
+    int rc = check_device(coords, &num_sms);
+    if (rc) return rc;
+    ihpr::launch_l1_from_coords(coords, gt, vis, have_depth, B, J, loss, static_cast<cudaStream_t>(stream));
+    g_launches = 1;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_coords_to_camera(const float* coords, const float* coords_flipped, const int* flip_perm, int B, int J, int D, int H, int W, const float* bbox,
                           const float* center_cam, const float* focal, const float* princpt, float bbox3d_depth, int root_idx, float* merged_out,
                           float* pixel_out, float* cam_out, void* stream) {

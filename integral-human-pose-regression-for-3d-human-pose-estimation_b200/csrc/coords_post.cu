@@ -101,4 +101,31 @@ void launch_coords_post(const float* coords, const float* flipped, const int* pe
     coords_post_kernel<<<(n + 127) / 128, 128, 0, s>>>(p);
 }
 
+// JointLocationLoss.forward on coordinates that already exist (common/nets/loss.py:49-52): the fused head (K3) produces the
+// coordinates without a heat-map, the masked L1 mean is this one small launch.  One block, fixed summation order:
+// thread t adds terms t, t + 256, ... in index order, then a fixed shared-memory tree -- bit-reproducible.
+__global__ void __launch_bounds__(256) l1_from_coords_kernel(const float* __restrict__ coords, const float* __restrict__ gt, const float* __restrict__ vis,
+                                                            const float* __restrict__ hd, int B, int J, float* __restrict__ loss) {
+    __shared__ float part[256];
+    const int n = B * J;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float* c = coords + (size_t)i * 3;
+        const float* g = gt + (size_t)i * 3;
+        const float v = vis[i], d = hd[i / J];
+        acc += (fabsf(c[0] - g[0]) * v + fabsf(c[1] - g[1]) * v + fabsf(c[2] - g[2]) * v * d) / 3.f;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = part[0] / (float)n;
+}
+
+void launch_l1_from_coords(const float* coords, const float* gt, const float* vis, const float* hd, int B, int J, float* loss, cudaStream_t s) {
+    l1_from_coords_kernel<<<1, 256, 0, s>>>(coords, gt, vis, hd, B, J, loss);
+}
+
 }  // namespace ihpr

@@ -322,6 +322,7 @@ void launch_patches(const unsigned char* images, const int* sizes, int B, int Hs
 void launch_joints(const double* joint_img, const double* joint_vis, const int* sizes, const double* trans, const double* scale, const int* do_flip,
                    const int* perm, int B, int J, int in_h, int in_w, int out_h, int out_w, int depth_dim, double bbox3d_depth, float* gt_coord,
                    float* gt_vis, cudaStream_t s);
+void launch_l1_from_coords(const float* coords, const float* gt, const float* vis, const float* hd, int B, int J, float* loss, cudaStream_t s);
 void launch_coords_post(const float* coords, const float* flipped, const int* perm, int B, int J, int D, int H, int W, const float* bbox,
                         const float* center, const float* focal, const float* princpt, float bbox3d_depth, int root, float* merged, float* pixel,
                         float* cam, cudaStream_t s);

@@ -330,9 +330,9 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             check(lib().ihpr_head_softargmax_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
                                                  coords.data_ptr(), stats.data_ptr(), stream))
-        # loss.py:49-52 on the (B, J, 3) coordinates: a handful of tiny ops
-        d = (coords - gt).abs() * vis.view(B, J, 1)
-        loss = ((d[..., 0] + d[..., 1] + d[..., 2] * hd.view(B, 1)) / 3.0).mean()
+            # loss.py:49-52 on the (B, J, 3) coordinates: one small launch
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            check(lib().ihpr_integral_l1_from_coords(coords.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), B, J, loss.data_ptr(), stream))
         ctx.save_for_backward(xb, wb, bf, coords, stats, gt, vis, hd)
         ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape))
         ctx.mark_non_differentiable(coords)
