@@ -87,9 +87,12 @@ int ihpr_integral_l1_bwd(const void *heat, int dtype, int B, int J, int D, int H
 
 /* Training step in ONE launch: JointLocationLoss forward (as ihpr_integral_l1_fwd) plus d loss / d heat for an
  * upstream gradient of 1, i.e. what main/train.py:67-71 (criterion + loss.backward()) produces.  Each
- * joint-volume is streamed from HBM once and re-read from L2 (DRAM traffic 2 N s instead of 3 N s); needs a
- * cooperative launch (partner CTAs of a joint-volume wait for each other).  Falls back to the two-kernel sequence
- * for small batches and for shapes only the scalar kernels handle -- same results either way. */
+ * joint-volume is streamed from HBM once and re-read from L2 (DRAM traffic 2 N s instead of 3 N s) by a cooperative
+ * launch whose partner CTAs wait for each other (K5); variant 7 selects K5c instead, which keeps the joint-volume in
+ * the shared memory of a thread-block cluster between the two passes (exactly 2 N s of DRAM traffic, but clusters of
+ * 8 / 16 CTAs leave 28 / 36 of a B200's 148 SMs idle, so it is slower and not the default).  Falls back to the
+ * two-kernel sequence for small batches and for shapes only the scalar kernels handle -- same results to rounding
+ * either way. */
 int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
                              const float *gt, const float *vis, const float *have_depth,
                              float *loss, float *coords, float *stats, void *grad_heat,
@@ -185,8 +188,9 @@ int ihpr_integral_l1_fwd_bwd_host(const void *heat_host, int dtype, int B, int J
 /* Frees the device buffers / streams the *_host entry point caches for `device`. */
 int ihpr_host_release(int device);
 
-/* Tuning / introspection (does not change results): kernel variant 0 = auto,
- * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads. */
+/* Tuning / introspection (does not change results beyond rounding): kernel variant 0 = auto,
+ * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads; for ihpr_integral_l1_fwd_bwd
+ * 7 = cluster-resident K5c where it applies, 9 = always the two-kernel sequence. */
 int ihpr_set_variant(int variant);
 int ihpr_get_variant(void);
 /* Number of kernels the LAST call on this thread launched (for bench.py's gpu_launches). */

@@ -223,9 +223,17 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     rc = check_device(heat, &num_sms);
     if (rc) return rc;
     const int S = v ? ihpr::fused_split(g, dtype) : 1;
-    // the fused kernel wants enough joint-volumes to keep every CTA group busy for a few rounds; otherwise (tiny
+    // K5c (joint-volume resident in a cluster's shared memory) is opt-in (variant 7): on B200 it is slower than K5 because
+    // clusters of 8 / 16 CTAs only fill 120 / 112 of the 148 SMs (profiles/r01_k5c_cluster_resident.txt)
+    ihpr::FusedClusterPlan plan = {0, 0, 0, 0};
+    if (v && variant == 7) plan = ihpr::fused_cluster_plan(g, dtype);
+    int CS = plan.cluster;
+    int ncl = CS ? ihpr::fused_cluster_capacity(dtype, CS) : 0;
+    if (ncl > B * J / 2) ncl = B * J / 2;
+    if (CS && ncl * CS * 2 < num_sms) CS = 0;              // too few joint-volumes (or clusters) to be worth a cluster launch
+    // the fused kernels want enough joint-volumes to keep every CTA group busy for a few rounds; otherwise (tiny
     // batches: everything fits in L2 anyway) or on the scalar path run K1 then K2
-    const bool fused = v && variant != 9 && (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S;
+    const bool fused = v && variant != 9 && (CS || (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S);
     if (!fused) {
         rc = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
         if (rc) return rc;
@@ -251,13 +259,17 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.f.maxslots = max_slots(D, H, W);
     p.grad_heat = grad_heat;
     p.S = S;
+    p.xc_chunks = p.xc_lag = 0;
     p.loss_scale = scale;
 #ifdef IHPR_TIMING_EXPERIMENTS
     p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;      // wrong results: only in builds made for timing experiments
 #else
     p.debug_no_exchange = 0;
 #endif
-    const cudaError_t le = ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream));
+    cudaError_t le = CS ? ihpr::launch_fused_cluster(p, dtype, plan, ncl, static_cast<cudaStream_t>(stream)) : cudaErrorLaunchOutOfResources;
+    if (CS && le != cudaSuccess) (void)cudaGetLastError();
+    if (le != cudaSuccess && (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S)
+        le = ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream));
     if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
         // the S CTAs of a joint-volume cannot be made co-resident right now (GPU shared with other work): same result
         // from the two-kernel path (still CUDA, still this library)

@@ -301,6 +301,7 @@ struct FusedParams {
     uint2* xslots;          // (R, kMaxSplit, 8) {value, tag} pairs: partials traded between the S CTAs of a volume
     int* epoch;             // launch counter in the workspace; tag = epoch + 1
     int S;                  // CTAs per joint-volume
+    int xc_chunks, xc_lag;  // K5c: chunks per CTA slice, chunks between the two passes
     float loss_scale;       // 1 / (3 * B * J)
     int debug_no_exchange;  // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_DEBUG_NOXCHG=1): skip the cross-CTA trade, WRONG results
 };
@@ -315,6 +316,15 @@ void launch_bwd(const BwdParams& p, int dtype, bool vec_ok, int variant, int num
 Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok, int variant);
 int fused_split(const Geometry& g, int dtype);
 cudaError_t launch_fused(const FusedParams& p, int dtype, int num_sms, cudaStream_t s);
+struct FusedClusterPlan {
+    int cluster;        // CTAs per joint-volume (cluster size); 0 = K5c does not apply
+    int chunk_bytes;    // ring stage size
+    int chunks;         // chunks per CTA slice
+    int lag;            // chunks between pass 1 and pass 2 of the same chunk
+};
+FusedClusterPlan fused_cluster_plan(const Geometry& g, int dtype);
+int fused_cluster_capacity(int dtype, int CS);
+cudaError_t launch_fused_cluster(const FusedParams& p, int dtype, const FusedClusterPlan& pl, int nclusters, cudaStream_t s);
 void launch_scale(void* grad, size_t n, int dtype, bool aligned, const float* grad_out, int num_sms, cudaStream_t s);
 void launch_patches(const unsigned char* images, const int* sizes, int B, int Hs, int Ws, const double* trans, const int* do_flip,
                     const float* color_scale, const float* mean, const float* stdv, int out_h, int out_w, float* out, int channels_last,

@@ -120,16 +120,21 @@ def test_oracle_seeded_shapes(shape, dist, dev):
     # (B, J, D, H, W, dtype): enough joint-volumes that ihpr_integral_l1_fwd_bwd takes the single-launch path (K5)
     (20, 16, 8, 8, 8, torch.float32),          # S = 1 (a joint-volume is one unit), partial chunks
     (9, 17, 32, 64, 64, torch.float32),        # S = 2 (512 KiB joint-volumes)
-    (10, 18, 64, 64, 64, torch.float32),       # S = 4 (1 MiB joint-volumes), the headline geometry
-    (10, 18, 64, 64, 64, torch.bfloat16),      # S = 2 in bf16
-    (4, 18, 128, 64, 64, torch.float32),       # S = 16 (2 MiB joint-volumes, D = 128)
+    (10, 18, 64, 64, 64, torch.float32),       # 1 MiB joint-volumes, the headline geometry: K5 S = 12; K5c clusters of 16
+    (10, 18, 64, 64, 64, torch.bfloat16),      # 512 KiB in bf16: K5c clusters of 8
+    (4, 18, 128, 64, 64, torch.float32),       # 2 MiB joint-volumes, D = 128: K5 S = 24 (too large for K5c)
+    (16, 17, 32, 64, 64, torch.bfloat16),      # 256 KiB: K5c clusters of 4
+    (24, 18, 32, 32, 32, torch.float32),       # 128 KiB: K5c clusters of 2
+    (5, 17, 64, 64, 64, torch.float32),        # 85 volumes over 7 clusters: uneven volume counts per cluster
     (6, 17, 48, 64, 64, torch.float32),        # 24 chunks per volume split 8 ways: 3 chunks per unit, J = 17
     (40, 8, 3, 5, 12, torch.float32),          # generic (non-fast) vector path inside K5
     (40, 8, 3, 5, 9, torch.float32),           # scalar shapes: falls back to K1 + K2
 ])
-def test_fused_forward_backward(case, dev):
+@pytest.mark.parametrize("variant", [0, 7])     # 0: the L2-resident K5; 7: the cluster-resident K5c where it applies, else K5
+def test_fused_forward_backward(case, variant, dev):
     import ihpr_b200
     B, J, D, H, W, dtype = case
+    ihpr_b200.set_variant(variant)
     heat = inputs.make_heat("randn3", B, J, D, H, W, seed=7)
     if dtype == torch.bfloat16:
         heat = torch.from_numpy(heat).to(torch.bfloat16).float().numpy()

@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <cuda_runtime.h>
 #include <time.h>
 #include <unistd.h>
@@ -75,11 +78,33 @@ int main(int argc, char** argv) {
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) { IK(fwd()); IK(bwd()); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tfb = ms * 1e3 / iters;
     if (verbose) { printf("K1/K2 timing done\n"); fflush(stdout); }
+    // keep K1 + K2's answer (coords, head and tail of the gradient) to cross-check the one-launch path against
+    const size_t probe = std::min<size_t>(R * N * es, 8u << 20);
+    std::vector<unsigned char> g_ref(2 * probe), g_fus(2 * probe);
+    std::vector<float> c_ref(R * 3), c_fus(R * 3);
+    CK(cudaMemcpy(g_ref.data(), grad, probe, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(g_ref.data() + probe, (char*)grad + R * N * es - probe, probe, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c_ref.data(), coords, R * 3 * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(grad, 0xff, R * N * es));
     for (int i = 0; i < 3; ++i) IK(fused());
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(fused()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tfu = ms * 1e3 / iters;
     float hl; CK(cudaMemcpy(&hl, loss, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(g_fus.data(), grad, probe, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(g_fus.data() + probe, (char*)grad + R * N * es - probe, probe, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c_fus.data(), coords, R * 3 * 4, cudaMemcpyDeviceToHost));
+    {
+        auto val = [&](const std::vector<unsigned char>& b, size_t i) -> double {
+            if (dtype == 0) return ((const float*)b.data())[i];
+            unsigned int u = ((unsigned int)((const unsigned short*)b.data())[i]) << 16; float f; memcpy(&f, &u, 4); return f;
+        };
+        double dmax = 0, amax = 0, cmax = 0;
+        for (size_t i = 0; i < 2 * probe / es; ++i) { double a = val(g_ref, i), b = val(g_fus, i); dmax = std::max(dmax, std::fabs(a - b)); amax = std::max(amax, std::fabs(a)); }
+        for (size_t i = 0; i < R * 3; ++i) cmax = std::max(cmax, (double)std::fabs(c_ref[i] - c_fus[i]));
+        printf("variant %d B %d dtype %d: one-launch vs K1+K2: max |dgrad| %.3e (max |grad| %.3e, rel %.2e), max |dcoords| %.2e\n", variant, B, dtype, dmax, amax,
+               amax > 0 ? dmax / amax : 0.0, cmax);
+    }
     const double V = (double)R * N * es;
     printf("variant %d B %d dtype %d: FUSED one-launch fwd+bwd %.1f us (%d launch; %.0f GB/s as 3V, %.0f GB/s as 2V, %.0f vol/s)\n", variant, B, dtype, tfu,
            ihpr_last_launch_count(), 3 * (double)R * N * es / tfu / 1e3, 2 * (double)R * N * es / tfu / 1e3, R / (tfu * 1e-6));
