@@ -41,7 +41,8 @@ def build_library(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        # IHPR_NVCC_EXTRA: extra flags for experiment builds (e.g. -DIHPR_TIMING_EXPERIMENTS, -DIHPR_DEBUG_HANG); never set for releases
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("IHPR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

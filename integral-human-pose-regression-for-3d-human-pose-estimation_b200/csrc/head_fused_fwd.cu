@@ -22,9 +22,7 @@
 // d loss / d heat = p * sum_c g_c (c(i) - coord_c) with the (m, l, coords) K3 saved, and written as bf16 in the heat-map's
 // own (B, J*D, H, W) layout -- so training never writes or reads the heat-map, only its gradient; dW / dX / dbias are then
 // plain library GEMMs on that gradient (host side, functional.py).
-#include <cuda.h>
-
-#include "ihpr_device.cuh"
+#include "head_tc.cuh"
 
 namespace ihpr {
 
@@ -34,8 +32,8 @@ constexpr int BN = 256;             // pixels per tile   = UMMA N
 constexpr int BK = 64;              // k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int STAGES_FWD = 4;       // ring of X k-blocks (K3)
 constexpr int STAGES_BWD = 3;       // K4 gives one stage up for the gradient staging buffers
-constexpr int STG_ROW = 80;         // K4 staging: 32 bf16 (64 B) per channel row + 16 B pad (conflict-free 16-byte stores)
-constexpr int STG_WARP = 32 * STG_ROW;
+constexpr int STG_ROW = 128;        // K4 staging: 64 bf16 (128 B) per channel row = one SWIZZLE_128B row of the TMA store
+constexpr int STG_WARP = 32 * STG_ROW;      // 4 KiB per epilogue warp: its 32 channels x 64 pixels of one accumulator stage
 constexpr int MAXKB = 4;            // K <= 256
 constexpr int A_KB_BYTES = BM * BK * 2;     // 16 KiB
 constexpr int B_KB_BYTES = BN * BK * 2;     // 32 KiB
@@ -60,76 +58,16 @@ struct Params {
     float loss_scale;       // 1 / (3 * B * J)
     __nv_bfloat16* grad_heat;   // (B, J*D, H*W) bf16 out: d loss / d heat-map, the heat-map itself is only ever a TMEM tile
     float* dbias_part;          // (B, 4, J*D) fp32 out or null: per-sample, per-column-split sums of the (unrounded) gradient = d loss / d bias partials
+    int dbg;                    // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_K4_DEBUG): 1 = no gradient store, 2 = no epilogue math -- WRONG results
 };
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start >> 4, LBO = 1 (unused),
-// SBO = 1024 B (8 rows x 128 B), version = 1 (Blackwell), layout type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, N = 256, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-        : "memory");
-}
-// Blackwell packed fp32 pairs (FFMA2 / FADD2 / FMUL2): two lanes of fp32 math per issue slot.  The epilogues are
-// issue-bound (ncu: the MMAs of a tile take fewer cycles than the epilogue needs issue slots), so every FMA / ADD over
-// the 32 columns a thread holds is done on (even, odd) column pairs.
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-          "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace tc;
+constexpr uint32_t kIdesc = make_idesc(BM, BN);
 
 template <bool BWD>
 __global__ void __launch_bounds__(32 * (4 + (BWD ? EPI_BWD : EPI_FWD)), 1)
-head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p) {
+head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                       const __grid_constant__ CUtensorMap map_g, const Params p) {
     constexpr int STAGES = BWD ? STAGES_BWD : STAGES_FWD;
     constexpr int EPI_WARPS = BWD ? EPI_BWD : EPI_FWD;
     constexpr int CS = EPI_WARPS / 4;           // column splits of the 256-column accumulator stage
@@ -139,7 +77,8 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                     // [KB][128 x 64] bf16
     uint8_t* sB = smem + MAXKB * A_KB_BYTES;                // [STAGES][256 x 64] bf16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_KB_BYTES);
+    uint8_t* stg = sB + STAGES * B_KB_BYTES;                // K4: [EPI_WARPS][32 rows x 128 B] gradient staging, 1024-byte aligned (SWIZZLE_128B)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (BWD ? EPI_WARPS * STG_WARP : 0));
     uint64_t* b_full = bars;                // [STAGES] TMA -> MMA
     uint64_t* b_empty = bars + STAGES;      // [STAGES] MMA -> TMA (tcgen05.commit)
     uint64_t* a_full = bars + 2 * STAGES;   // [1]
@@ -148,8 +87,6 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     uint64_t* t_empty = t_full + 2;         // [2]      epilogue -> MMA: accumulator stage drained (EPI_WARPS arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_MAX][8]
-    // K4: [EPI_WARPS][32 rows][STG_ROW] gradient staging, 16-byte aligned
-    uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(red + 2 * EPI_MAX) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.B * p.MT;
@@ -205,7 +142,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                         const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * B_KB_BYTES));
 #pragma unroll
                         for (int k16 = 0; k16 < BK / 16; ++k16)      // +32 B per K=16 step inside the 128 B swizzle row: +2 in the (>>4) address field
-                            umma(tmem_d, ad + 2 * k16, bd + 2 * k16, (uint32_t)((kb | k16) != 0));
+                            umma(tmem_d, ad + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((kb | k16) != 0));
                         tc_commit(b_empty + s);          // frees the X stage when these MMAs have read it
                     }
                     tc_commit(t_full + as);              // accumulator stage complete
@@ -239,17 +176,28 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                 const float gz = sc * sgn(cz - __ldg(p.gt + 3 * r + 2)) * __ldg(p.have_depth + b);
                 const float k0 = bias2 - safe_c(m);
                 const float tz = gz * (zf - cz);
+                static_assert(!BWD || CW == 64, "K4: one epilogue warp owns 64 pixels = one 128-byte staging row per channel");
                 uint8_t* wstg = stg + e * STG_WARP;
+                uint8_t* srow = wstg + lane * STG_ROW;
+                const int sw = lane & 7;                     // SWIZZLE_128B: 16-byte chunk index ^= row & 7
                 float dsum = 0.f;
                 for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(t_full + as, aph);
                     tc_fence_after();
+                    // the TMA store of the previous tile has read this warp's staging buffer
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
                     const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * CW;
 #pragma unroll 1
                     for (int j = 0; j < CW / 32; ++j) {
                         float v[32];
                         tmem_ld32(tbase + j * 32, v);
+                        if (j == CW / 32 - 1) {             // the accumulator stage is in registers: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_empty + as);
+                        }
                         const uint32_t pix = (uint32_t)(nt * BN + ch * CW + j * 32);
                         const uint32_t y = fdiv(pix, divW);
                         const float base = fmaf(gy, u2f(y) - cy, fmaf(gx, u2f(pix - y * divW.d) - cx, tz));
@@ -257,6 +205,12 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                         const uint64_t l2e2 = pk2(kLog2e, kLog2e), k02 = pk2(k0, k0);
                         const uint64_t b01 = pk2(base, base + gx), gx22 = pk2(2.f * gx, 2.f * gx);
                         uint64_t ds2 = pk2(0.f, 0.f);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                        if (p.dbg & 2) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(v[2 * i]) ^ __float_as_uint(v[2 * i + 1]);
+                        } else
+#endif
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float t0, t1, d0, d1;
@@ -272,27 +226,35 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                             up2(ds2, da, db);
                             dsum += da + db;
                         }
-                        // this thread's 32 pixels (64 B) of its channel row go to the warp's staging tile and leave as
-                        // 64-byte row segments, 4 lanes per channel row (the first version stored 16-byte pieces at an
-                        // 8 KiB stride straight from the registers: 154 us instead of 107 us at B = 32)
-                        uint8_t* srow = wstg + lane * STG_ROW;
+                        // this thread's 32 pixels (64 B) of its channel row: four 16-byte chunks of the row's swizzled 128 bytes
+                        // (conflict-free: the 8 lanes of a store phase hit 8 different chunk positions)
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<uint4*>(srow + i * 16) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = i * 8 + (lane >> 2);
-                            const int crow = mt * BM + qd * 32 + row;
-                            const uint4 val = *reinterpret_cast<const uint4*>(wstg + row * STG_ROW + (lane & 3) * 16);
-                            if (crow < p.J * p.D)
-                                st_stream16(p.grad_heat + ((size_t)b * p.J * p.D + crow) * ((size_t)p.H * p.W) + pix + (lane & 3) * 8, val);
-                        }
-                        __syncwarp();
+                            sts16(srow + (((j * 4 + i) ^ sw) << 4), make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
                     }
-                    tc_fence_before();
+                    // 32 channels x 64 pixels leave as ONE TMA tile store: full 128-byte lines per channel row, rows beyond J*D
+                    // clipped by the tensor map (the first version stored 16-byte pieces at an 8 KiB stride from registers: 154 us
+                    // at B = 32; staging + 64-byte STG segments: 103 us)
+                    fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + as);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                    if (p.dbg & 1) continue;
+#endif
+                    if (lane == 0) {
+#ifdef IHPR_TIMING_EXPERIMENTS
+                        if (p.dbg & 16) {       // blocked layout: this warp's 4 KiB tile to one contiguous block (WRONG layout, timing only)
+                            uint8_t* dst = reinterpret_cast<uint8_t*>(p.grad_heat) + ((((size_t)item * p.NT + nt) * EPI_WARPS + e) << 12);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(dst), "r"(smem_u32(wstg)) : "memory");
+                        } else if (p.dbg & 12) {
+                            uint64_t pol;
+                            if (p.dbg & 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+                            else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                            tma_store_3d_hint(&map_g, wstg, nt * BN + ch * CW, mt * BM + qd * 32, b, pol);
+                        } else
+#endif
+                        tma_store_3d(&map_g, wstg, nt * BN + ch * CW, mt * BM + qd * 32, b);
+                        tma_store_commit();
+                    }
                 }
                 if (p.dbias_part && valid) p.dbias_part[((size_t)b * CS + ch) * (p.J * p.D) + c] = dsum;
                 continue;
@@ -377,6 +339,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
         }
     }
 
+    if (BWD && warp >= 4 && lane == 0) tma_store_wait_all();       // gradient tiles are out before the CTA (and its shared memory) goes away
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -385,32 +348,6 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
 }  // namespace k3
 
 // ---- host side --------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// 2-D bf16 tensor [rows][K] (K contiguous), box [box_rows][64], SWIZZLE_128B
-static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {K, rows};
-    const cuuint64_t strides[1] = {K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)k3::BK, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
                               float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
                               float* dbias_part, int num_sms, cudaStream_t s) {
@@ -424,17 +361,23 @@ const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bi
     p.loss_scale = 1.0f / (3.0f * (float)B * (float)J);
     p.grad_heat = static_cast<__nv_bfloat16*>(grad_heat);
     p.dbias_part = dbias_part;
+    p.dbg = 0;
+#ifdef IHPR_TIMING_EXPERIMENTS
+    if (const char* e = getenv("IHPR_K4_DEBUG")) p.dbg = atoi(e);
+#endif
     const bool bwd = grad_heat != nullptr;
-    CUtensorMap map_w, map_x;
-    if (!make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
-    if (!make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
+    CUtensorMap map_w, map_x, map_g;
+    memset(&map_g, 0, sizeof(map_g));
+    if (!tc::make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
+    if (!tc::make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
+    if (bwd && !tc::make_map_grad(&map_g, grad_heat, (uint64_t)B, (uint64_t)J * D, (uint64_t)H * W, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return "cuTensorMapEncodeTiled failed for the gradient";
     const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + (bwd ? k3::STAGES_BWD : k3::STAGES_FWD) * k3::B_KB_BYTES + 32 * sizeof(uint64_t) +
                         2 * k3::EPI_MAX * 8 * sizeof(float) + (bwd ? k3::EPI_BWD * k3::STG_WARP : 0);
     auto kern = bwd ? k3::head_softargmax_kernel<true> : k3::head_softargmax_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed";
     int grid = B * p.MT;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, 32 * (4 + (bwd ? k3::EPI_BWD : k3::EPI_FWD)), smem, s>>>(map_w, map_x, p);
+    kern<<<grid, 32 * (4 + (bwd ? k3::EPI_BWD : k3::EPI_FWD)), smem, s>>>(map_w, map_x, map_g, p);
     return nullptr;
 }
 

@@ -379,7 +379,13 @@ def test_fused_head_conv_soft_argmax(case, dev):
         ihpr_b200.fused_head_soft_argmax(xd.requires_grad_(True), wt.to(dev), bias.to(dev), J)
 
 
-@pytest.mark.parametrize("case", [(2, 18, 64, 64, 64, 256), (3, 5, 32, 32, 32, 128)])
+@pytest.mark.parametrize("case", [
+    (2, 18, 64, 64, 64, 256),       # the headline head: 1152 channels = 9 tiles of 128
+    (3, 5, 32, 32, 32, 128),
+    (2, 17, 64, 64, 64, 256),       # J = 17: 1088 channels, the last tile has 64 live channels (rows beyond J*D clipped by the TMA store)
+    (200, 2, 32, 8, 32, 64),        # more (sample, channel-tile) items than SMs: persistent CTAs walk several items
+    (1, 3, 128, 16, 32, 192),       # D = 128: a joint spans a whole channel tile; K = 192
+])
 def test_fused_head_training_step(case, dev):
     """K3 + K4: loss and parameter / activation gradients of final_layer + JointLocationLoss without a stored heat-map,
     vs torch autograd through conv2d (fp32, same bf16-rounded operands) + the reference criterion restatement.
