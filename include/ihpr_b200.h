@@ -190,7 +190,8 @@ int ihpr_host_release(int device);
 
 /* Tuning / introspection (does not change results beyond rounding): kernel variant 0 = auto,
  * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads; for ihpr_integral_l1_fwd_bwd
- * 7 = cluster-resident K5c where it applies, 9 = always the two-kernel sequence. */
+ * 7 = cluster-resident K5c where it applies, 9 = always the two-kernel sequence; for the fused-head entries
+ * 5 = the SM-pair (tcgen05 cta_group::2) form of K3 / K4 (bit-identical results, slower on B200: profiles/r01_ncu_K4.txt). */
 int ihpr_set_variant(int variant);
 int ihpr_get_variant(void);
 /* Number of kernels the LAST call on this thread launched (for bench.py's gpu_launches). */

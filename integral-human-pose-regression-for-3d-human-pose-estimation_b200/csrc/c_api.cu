@@ -407,8 +407,12 @@ static int head_common(const void* x_nhwc, const void* weight, const float* bias
     int num_sms = 0;
     int rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
-    const char* err = ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part, num_sms,
-                                              static_cast<cudaStream_t>(stream));
+    // variant 5: the SM-pair (cta_group::2) form of K3 / K4
+    const bool pairs = g_variant.load(std::memory_order_relaxed) == 5 && num_sms >= 2;
+    const char* err = pairs ? ihpr::launch_head_fused_pair(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat,
+                                                           dbias_part, num_sms, static_cast<cudaStream_t>(stream))
+                            : ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part,
+                                                      num_sms, static_cast<cudaStream_t>(stream));
     if (err) return fail(IHPR_ECUDA, "%s", err);
     g_launches = 1;
     IHPR_CUDA(cudaGetLastError());

@@ -1,72 +1,65 @@
-// head_fused_fwd.cu -- K3: HeadNet.final_layer (1x1 conv, /root/reference/main/model.py:14-20,42) fused with the
-// 3-D soft-argmax (/root/reference/common/nets/loss.py:13-34): the J*D x H x W heat-map never exists in HBM.
+// head_fused_pair.cu -- K3 / K4 on SM pairs (tcgen05 cta_group::2): the fused 1x1 conv + soft-argmax forward and the heat-map
+// gradient of head_fused_fwd.cu with HALF the activation traffic per SM.
 //
-// Per sample b the 1x1 conv is the GEMM  Hm[c, n] = sum_k Wt[c, k] * X[b, n, k] + bias[c]
-//   c = j*D + d  (M = J*D output channels),  n = y*W + x (N = H*W pixels),  k < K = 256 input channels,
-// on the 5th-generation tensor cores:  tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 (bf16 in, fp32 accumulate),
-// both operands K-major in shared memory (X is taken in NHWC / channels_last, the layout the cuDNN deconv emits), staged
-// by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B), accumulator in TMEM (2 stages x 256 columns, so the MMA of the next
-// pixel tile overlaps the epilogue of this one).  TMEM lane = output channel = (joint, z); TMEM column = pixel (y, x).
-//
-// Work item = (sample b, 128-channel tile).  One persistent CTA per SM walks items b*MT + mt, so the CTAs that share a
-// sample run together and its X tiles come out of L2.  Per item the Wt tile (128 x K bf16, 64 KiB) is loaded once and
-// the 16 pixel tiles of X[b] stream through a 4-stage ring of 256 x 64 k-blocks.
-//
-// Epilogue (16 warps in K3, 8 in K4; warp%4 selects the TMEM lane quarter, warp/4 the column split): tcgen05.ld 32 columns at a time,
-// online softmax over pixels per lane with the same lazy re-base as K1, sum p, sum p*x, sum p*y per lane (z is the
-// lane's constant); after the last pixel tile the D lanes x 2 halves of a joint are merged and coords / stats written.
-//
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator, 4.. = epilogue.
-//
-// K4 (template BWD = true) is the same GEMM with another epilogue: the heat-map tile is recomputed in TMEM, turned into
-// d loss / d heat = p * sum_c g_c (c(i) - coord_c) with the (m, l, coords) K3 saved, and written as bf16 in the heat-map's
-// own (B, J*D, H, W) layout -- so training never writes or reads the heat-map, only its gradient; dW / dX / dbias are then
-// plain library GEMMs on that gradient (host side, functional.py).
+// Same math, same epilogues, same outputs as head_fused_fwd.cu (HeadNet.final_layer, /root/reference/main/model.py:14-20,42, fused with
+// soft_argmax / JointLocationLoss and its backward, /root/reference/common/nets/loss.py:13-52).  What changes is who feeds the
+// tensor cores: profiles/r01_ncu_K4.txt shows both kernels pay for re-reading the activations X[b] from L2 once per 128-channel
+// tile.  Here the two CTAs of a cluster own two ADJACENT channel tiles (mt = 2*mtp + rank) of the same sample and run ONE
+// 256 x 256 x 16 UMMA per k-step: each CTA loads its own Wt tile (A, 128 rows) and only HALF of the X tile (B: 128 of the 256
+// pixels, 16 KiB per k-block instead of 32), the tensor cores read both halves across the pair, and each CTA ends up with its
+// own 128 channels x 256 pixels accumulator in its own TMEM -- so the epilogues are untouched.  The halved stages buy a deeper
+// ring (8 / 6 k-blocks in flight instead of 4 / 3).
+//   leader (rank 0): issues every MMA; its b_full / a_full barriers count the bytes of BOTH CTAs' TMA loads
+//                    (cp.async.bulk.tensor ... .cta_group::2 may complete on the peer's barrier); its t_empty barriers collect
+//                    the epilogue warps of both CTAs (the peer's arrive remotely)
+//   both           : tcgen05.commit ... .multicast::cluster frees the X stage / Wt tile and publishes the accumulator stage in
+//                    both CTAs at once
+// With an odd number of channel tiles (J*D = 1152 -> 9) the last pair has a dead CTA whose Wt tile is all zero-fill.
 #include "head_tc.cuh"
 
 namespace ihpr {
 
-namespace k3 {
-constexpr int BM = 128;             // channels per tile = UMMA M
-constexpr int BN = 256;             // pixels per tile   = UMMA N
-constexpr int BK = 64;              // k-block: 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int STAGES_FWD = 4;       // ring of X k-blocks (K3); a 5th stage fits and changes nothing (68.0 us at B = 32 either way)
-constexpr int STAGES_BWD = 3;       // K4 gives one stage up for the gradient staging buffers
-constexpr int STG_ROW = 128;        // K4 staging: 64 bf16 (128 B) per channel row = one SWIZZLE_128B row of the TMA store
-constexpr int STG_WARP = 32 * STG_ROW;      // 4 KiB per epilogue warp: its 32 channels x 64 pixels of one accumulator stage
-constexpr int MAXKB = 4;            // K <= 256
+namespace k3p {
+using namespace tc;
+
+constexpr int BM = 128;             // channels per CTA = its half of the UMMA's M = 256
+constexpr int BN = 256;             // pixels per tile = UMMA N
+constexpr int BNH = BN / 2;         // pixels of the X tile this CTA loads
+constexpr int BK = 64;
+constexpr int STAGES_FWD = 8;
+constexpr int STAGES_BWD = 6;
+constexpr int STG_ROW = 128;
+constexpr int STG_WARP = 32 * STG_ROW;
+constexpr int MAXKB = 4;
 constexpr int A_KB_BYTES = BM * BK * 2;     // 16 KiB
-constexpr int B_KB_BYTES = BN * BK * 2;     // 32 KiB
-constexpr int EPI_FWD = 16;          // K3 epilogue warps: 4 per TMEM lane quarter, 64 columns each
-constexpr int EPI_BWD = 16;          // K4: also 4 per lane quarter -- its epilogue is latency-bound (TMEM load -> math -> staging -> store)
+constexpr int B_KB_BYTES = BNH * BK * 2;    // 16 KiB: this CTA's half of a k-block
+constexpr int EPI_FWD = 16;
+constexpr int EPI_BWD = 16;
 constexpr int EPI_MAX = 16;
-constexpr uint32_t TMEM_COLS = 512;         // 2 accumulator stages x 256 fp32 columns
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t kIdesc = make_idesc(2 * BM, BN);
 
 struct Params {
     int B, K, J, D, H, W;
     int MT;                 // channel tiles = ceil(J*D / 128)
+    int MTP;                // channel-tile pairs = ceil(MT / 2)
     int NT;                 // pixel tiles = H*W / 256
     int KB;                 // k-blocks = K / 64
-    const float* bias;      // (J*D)
-    float* coords;          // (B, J, 3)   forward: out; backward: in
-    float* stats;           // (B, J, 2)   forward: out (or null); backward: in
-    // backward (K4) only
-    const float* gt;        // (B, J, 3)
-    const float* vis;       // (B, J)
-    const float* have_depth;// (B)
-    const float* grad_out;  // device scalar
-    float loss_scale;       // 1 / (3 * B * J)
-    __nv_bfloat16* grad_heat;   // (B, J*D, H*W) bf16 out: d loss / d heat-map, the heat-map itself is only ever a TMEM tile
-    float* dbias_part;          // (B, 4, J*D) fp32 out or null: per-sample, per-column-split sums of the (unrounded) gradient = d loss / d bias partials
-    int dbg;                    // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_K4_DEBUG): 1 = no gradient store, 2 = no epilogue math -- WRONG results
+    const float* bias;
+    float* coords;
+    float* stats;
+    const float* gt;
+    const float* vis;
+    const float* have_depth;
+    const float* grad_out;
+    float loss_scale;
+    __nv_bfloat16* grad_heat;
+    float* dbias_part;
 };
-
-using namespace tc;
-constexpr uint32_t kIdesc = make_idesc(BM, BN);
 
 template <bool BWD>
 __global__ void __launch_bounds__(32 * (4 + (BWD ? EPI_BWD : EPI_FWD)), 1)
-head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                        const __grid_constant__ CUtensorMap map_g, const Params p) {
     constexpr int STAGES = BWD ? STAGES_BWD : STAGES_FWD;
     constexpr int EPI_WARPS = BWD ? EPI_BWD : EPI_FWD;
@@ -89,50 +82,55 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     float(*red)[8] = reinterpret_cast<float(*)[8]>(tmem_slot + 2);      // [2][EPI_MAX][8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.B * p.MT;
+    const uint32_t rank = pair_rank();           // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int items = p.B * p.MTP;               // (sample, channel-tile pair)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         mbar_init(a_full, 1); mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 2 * EPI_WARPS); }
         mbar_fence_init();
     }
-    if (warp == 2) {        // TMEM allocation: one warp, result through shared memory
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 2) {        // TMEM allocation: one warp in each CTA of the pair, same columns in both
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    pair_sync();            // the peer's barriers exist and its TMEM is allocated before anything is signalled across the pair
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs: own Wt tile, own half of every X k-block; bytes counted by the leader) =================
         if (lane == 0) {
+            const uint32_t a_full_l = pair_addr(a_full, 0);
             uint32_t it = 0, n_item = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-                const int b = item / p.MT, mt = item - b * p.MT;
+            for (int item = pair; item < items; item += npairs, ++n_item) {
+                const int b = item / p.MTP, mt = 2 * (item - b * p.MTP) + (int)rank;
                 mbar_wait(a_empty, (n_item & 1) ^ 1);
-                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_KB_BYTES));
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &map_w, kb * BK, mt * BM, a_full);
+                if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(2 * p.KB * A_KB_BYTES));
+                for (int kb = 0; kb < p.KB; ++kb)       // a dead tile (mt == MT) is all out of bounds: zero-filled
+                    tma_load_2d_pair(sA + kb * A_KB_BYTES, &map_w, kb * BK, mt * BM, a_full_l);
                 for (int nt = 0; nt < p.NT; ++nt)
                     for (int kb = 0; kb < p.KB; ++kb, ++it) {
                         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(b_empty + s, ph ^ 1);
-                        mbar_expect_tx(b_full + s, (uint32_t)B_KB_BYTES);
-                        tma_load_2d(sB + s * B_KB_BYTES, &map_x, kb * BK, b * p.NT * BN + nt * BN, b_full + s);
+                        if (rank == 0) mbar_expect_tx(b_full + s, (uint32_t)(2 * B_KB_BYTES));
+                        tma_load_2d_pair(sB + s * B_KB_BYTES, &map_x, kb * BK, (b * p.NT + nt) * BN + (int)rank * BNH, pair_addr(b_full + s, 0));
                     }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (leader only) =================
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, n_item = 0, acc_it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+            for (int item = pair; item < items; item += npairs, ++n_item) {
                 mbar_wait(a_full, n_item & 1);
                 for (int nt = 0; nt < p.NT; ++nt, ++acc_it) {
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-                    mbar_wait(t_empty + as, aph ^ 1);
+                    mbar_wait(t_empty + as, aph ^ 1);       // the epilogue warps of BOTH CTAs have drained this stage
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * BN;
                     for (int kb = 0; kb < p.KB; ++kb, ++it) {
@@ -141,13 +139,14 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                         tc_fence_after();
                         const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * B_KB_BYTES));
 #pragma unroll
-                        for (int k16 = 0; k16 < BK / 16; ++k16)      // +32 B per K=16 step inside the 128 B swizzle row: +2 in the (>>4) address field
-                            umma(tmem_d, ad + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((kb | k16) != 0));
-                        tc_commit(b_empty + s);          // frees the X stage when these MMAs have read it
+                        for (int k16 = 0; k16 < BK / 16; ++k16)
+                            umma_pair(tmem_d, ad + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((kb | k16) != 0));
+                        tc_commit_pair(b_empty + s);         // frees the X stage in both CTAs
                     }
-                    tc_commit(t_full + as);              // accumulator stage complete
+                    tc_commit_pair(t_full + as);             // accumulator stage complete in both CTAs
                 }
-                tc_commit(a_empty);                      // Wt tile may be overwritten
+                // Wt tiles may be overwritten; not after the last item: nobody waits for it and the peer may already be gone
+                if (item + npairs < items) tc_commit_pair(a_empty);
             }
         }
     } else if (warp >= 4) {
@@ -158,8 +157,14 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
         const int lane_c = qd * 32 + lane;       // channel within the tile = TMEM lane
         const FastDiv divW = make_fastdiv((uint32_t)p.W);
         uint32_t acc_it = 0, n_item = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-            const int b = item / p.MT, mt = item - b * p.MT;
+        const uint32_t t_empty_l0 = pair_addr(t_empty, 0), t_empty_l1 = pair_addr(t_empty + 1, 0);
+        auto release_stage = [&](uint32_t as) {     // this warp is done with accumulator stage `as`: tell the leader's MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(as ? t_empty_l1 : t_empty_l0);
+        };
+        for (int item = pair; item < items; item += npairs, ++n_item) {
+            const int b = item / p.MTP, mt = 2 * (item - b * p.MTP) + (int)rank;
             const int c = mt * BM + lane_c;                      // output channel
             const bool valid = c < p.J * p.D;
             const float bias_f = valid ? __ldg(p.bias + c) : 0.f;
@@ -185,6 +190,10 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
                     mbar_wait(t_full + as, aph);
                     tc_fence_after();
+                    if (mt >= p.MT) {               // dead CTA of the last pair: nothing to compute or store
+                        release_stage(as);
+                        continue;
+                    }
                     // the TMA store of the previous tile has read this warp's staging buffer
                     if (lane == 0) tma_store_wait_read();
                     __syncwarp();
@@ -193,11 +202,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     for (int j = 0; j < CW / 32; ++j) {
                         float v[32];
                         tmem_ld32(tbase + j * 32, v);
-                        if (j == CW / 32 - 1) {             // the accumulator stage is in registers: hand it back to the MMA warp
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(t_empty + as);
-                        }
+                        if (j == CW / 32 - 1) release_stage(as);     // the accumulator stage is in registers: hand it back to the MMA warp
                         const uint32_t pix = (uint32_t)(nt * BN + ch * CW + j * 32);
                         const uint32_t y = fdiv(pix, divW);
                         const float base = fmaf(gy, u2f(y) - cy, fmaf(gx, u2f(pix - y * divW.d) - cx, tz));
@@ -302,9 +307,7 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
                     a.sx += fmaf(x0f, s, w);
                     a.sy = fmaf(yf, s, a.sy);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + as);
+                release_stage(as);
             }
             // ---- merge the lanes (z) and the two column halves of each joint, write coords / stats
             if (!valid) a.reset();
@@ -342,42 +345,52 @@ head_softargmax_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_c
     if (BWD && warp >= 4 && lane == 0) tma_store_wait_all();       // gradient tiles are out before the CTA (and its shared memory) goes away
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    pair_sync();            // both CTAs are done with the pair's MMAs, barriers and TMEM
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
-}  // namespace k3
+}  // namespace k3p
 
-// ---- host side --------------------------------------------------------------------------------------------------
-const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
-                              float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
-                              float* dbias_part, int num_sms, cudaStream_t s) {
-    k3::Params p;
+const char* launch_head_fused_pair(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
+                                   float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
+                                   float* dbias_part, int num_sms, cudaStream_t s) {
+    k3p::Params p;
     p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
-    p.MT = (J * D + k3::BM - 1) / k3::BM;
-    p.NT = H * W / k3::BN;
-    p.KB = K / k3::BK;
+    p.MT = (J * D + k3p::BM - 1) / k3p::BM;
+    p.MTP = (p.MT + 1) / 2;
+    p.NT = H * W / k3p::BN;
+    p.KB = K / k3p::BK;
     p.bias = bias; p.coords = coords; p.stats = stats;
     p.gt = gt; p.vis = vis; p.have_depth = have_depth; p.grad_out = grad_out;
     p.loss_scale = 1.0f / (3.0f * (float)B * (float)J);
     p.grad_heat = static_cast<__nv_bfloat16*>(grad_heat);
     p.dbias_part = dbias_part;
-    p.dbg = 0;
-#ifdef IHPR_TIMING_EXPERIMENTS
-    if (const char* e = getenv("IHPR_K4_DEBUG")) p.dbg = atoi(e);
-#endif
     const bool bwd = grad_heat != nullptr;
     CUtensorMap map_w, map_x, map_g;
     memset(&map_g, 0, sizeof(map_g));
-    if (!tc::make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3::BM)) return "cuTensorMapEncodeTiled failed for the weight";
-    if (!tc::make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3::BN)) return "cuTensorMapEncodeTiled failed for the activations";
-    if (bwd && !tc::make_map_grad(&map_g, grad_heat, (uint64_t)B, (uint64_t)J * D, (uint64_t)H * W, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return "cuTensorMapEncodeTiled failed for the gradient";
-    const size_t smem = 1024 + k3::MAXKB * k3::A_KB_BYTES + (bwd ? k3::STAGES_BWD : k3::STAGES_FWD) * k3::B_KB_BYTES + 32 * sizeof(uint64_t) +
-                        2 * k3::EPI_MAX * 8 * sizeof(float) + (bwd ? k3::EPI_BWD * k3::STG_WARP : 0);
-    auto kern = bwd ? k3::head_softargmax_kernel<true> : k3::head_softargmax_kernel<false>;
+    if (!tc::make_map(&map_w, w, (uint64_t)J * D, (uint64_t)K, k3p::BM)) return "cuTensorMapEncodeTiled failed for the weight";
+    if (!tc::make_map(&map_x, x_nhwc, (uint64_t)B * H * W, (uint64_t)K, k3p::BNH)) return "cuTensorMapEncodeTiled failed for the activations";
+    if (bwd && !tc::make_map_grad(&map_g, grad_heat, (uint64_t)B, (uint64_t)J * D, (uint64_t)H * W, 64, CU_TENSOR_MAP_SWIZZLE_128B))
+        return "cuTensorMapEncodeTiled failed for the gradient";
+    const size_t smem = 1024 + k3p::MAXKB * k3p::A_KB_BYTES + (bwd ? k3p::STAGES_BWD : k3p::STAGES_FWD) * k3p::B_KB_BYTES + 32 * sizeof(uint64_t) +
+                        2 * k3p::EPI_MAX * 8 * sizeof(float) + (bwd ? k3p::EPI_BWD * k3p::STG_WARP : 0);
+    auto kern = bwd ? k3p::head_softargmax_pair_kernel<true> : k3p::head_softargmax_pair_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed";
-    int grid = B * p.MT;
-    if (grid > num_sms) grid = num_sms;
-    kern<<<grid, 32 * (4 + (bwd ? k3::EPI_BWD : k3::EPI_FWD)), smem, s>>>(map_w, map_x, map_g, p);
+    int npairs = B * p.MTP;
+    if (npairs > num_sms / 2) npairs = num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * npairs));
+    cfg.blockDim = dim3(32 * (4 + (bwd ? k3p::EPI_BWD : k3p::EPI_FWD)));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, map_w, map_x, map_g, p) != cudaSuccess) return "cluster launch of the SM-pair fused head failed";
     return nullptr;
 }
 

@@ -1,6 +1,6 @@
-// head_tc.cuh -- tcgen05 / TMEM / TMA building blocks shared by the fused-head kernels (K3 / K4 in head_fused_fwd.cu, K4 in its
-// 256-channel form in head_fused_bwd2.cu): TMA tile loads / stores, UMMA descriptors and issue, TMEM loads, packed fp32x2
-// math, tensor-map encoding.  sm_100a only.
+// head_tc.cuh -- tcgen05 / TMEM / TMA building blocks shared by the fused-head kernels (K3 / K4 in head_fused_fwd.cu, their
+// SM-pair form in head_fused_pair.cu): TMA tile loads / stores, UMMA descriptors and issue (cta_group::1 and ::2), TMEM
+// loads, packed fp32x2 math, tensor-map encoding.  sm_100a only.
 #pragma once
 #include <cuda.h>
 
@@ -16,6 +16,37 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
+}
+// ---- SM pair (cta_group::2): the two CTAs of a cluster run ONE 256-row UMMA; rank 0 issues it
+__device__ __forceinline__ uint32_t pair_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void pair_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same object in CTA `rank` of the pair
+__device__ __forceinline__ uint32_t pair_addr(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+// tile load into THIS CTA's shared memory whose bytes are counted on an mbarrier of either CTA of the pair (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+                 : "memory");
+}
+// arrive on the same barrier in BOTH CTAs when every MMA issued so far has completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // shared -> global tile store (bulk-group completion); coordinates (pixel, channel, sample) of the 3-D gradient map
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
@@ -52,6 +83,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }

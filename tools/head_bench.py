@@ -13,8 +13,10 @@ ap.add_argument("--D", type=int, default=64)
 ap.add_argument("--K", type=int, default=256)
 ap.add_argument("--hw", type=int, default=64)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--variant", type=int, default=0, help="5 = SM-pair (cta_group::2) form of K3 / K4")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
+ihpr_b200.set_variant(a.variant)
 B, J, D, K, H, W = a.B, a.J, a.D, a.K, a.hw, a.hw
 x = torch.randn(B, K, H, W, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 conv = torch.nn.Conv2d(K, J * D, 1).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
@@ -57,7 +59,7 @@ t_k4 = timeit(lambda: check(lib().ihpr_head_integral_l1_bwd(x.data_ptr(), wb.dat
 with torch.no_grad():
     c2 = ihpr_b200.soft_argmax(conv(x).float(), J)
 flop = 2.0 * B * J * D * K * H * W
-print(json.dumps({"B": B, "J": J, "D": D, "K": K, "HW": H, "fused_us": round(t_fused, 1), "fused_TFLOPs": round(flop / t_fused / 1e6, 1),
+print(json.dumps({"variant": a.variant, "B": B, "J": J, "D": D, "K": K, "HW": H, "fused_us": round(t_fused, 1), "fused_TFLOPs": round(flop / t_fused / 1e6, 1),
                   "k4_bwd_us": round(t_k4, 1), "k4_TFLOPs": round(flop / t_k4 / 1e6, 1), "k4_write_GBps": round(B * J * D * H * W * 2 / t_k4 / 1e3, 1),
                   "conv_us": round(t_conv, 1), "k1_bf16_us": round(t_k1, 1), "conv_plus_k1_us": round(t_unf, 1),
                   "speedup": round(t_unf / t_fused, 2), "max_coord_diff_vs_unfused": float((c1 - c2).abs().max())}))
