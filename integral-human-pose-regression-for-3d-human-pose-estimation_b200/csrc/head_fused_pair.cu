@@ -272,16 +272,23 @@ head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __g
                 mbar_wait(t_full + as, aph);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + as * BN + ch * CW;
-#pragma unroll 1
-                for (int j = 0; j < CW / 32; ++j) {
-                    float v[32];
-                    tmem_ld32(tbase + j * 32, v);
-                    const uint32_t pix = (uint32_t)(nt * BN + ch * CW + j * 32);     // first pixel of this 32-column group
+                // 16 columns at a time, software-pipelined: the tcgen05.ld of chunk q+1 is in flight while chunk q is reduced, so the
+                // TMEM load latency and the max chain of one chunk hide behind the exponentials of another (the 4 epilogue warps of
+                // an SM sub-partition start every tile in lockstep; with 32-column loads the MUFU idled during every load)
+                uint32_t ra[16], rb[16];
+                tmem_ld16_issue(tbase, ra);
+                tmem_ld16_wait(ra);
+#pragma unroll
+                for (int q = 0; q < CW / 16; ++q) {
+                    uint32_t(&cur)[16] = (q & 1) ? rb : ra;
+                    uint32_t(&nxt)[16] = (q & 1) ? ra : rb;
+                    if (q + 1 < CW / 16) tmem_ld16_issue(tbase + (q + 1) * 16, nxt);
+                    const uint32_t pix = (uint32_t)(nt * BN + ch * CW + q * 16);     // first pixel of this 16-column chunk (W % 32 == 0: one image row)
                     const uint32_t y = fdiv(pix, divW);
                     const float yf = u2f(y), x0f = u2f(pix - y * divW.d);
-                    float cmax = v[0];
+                    float cmax = __uint_as_float(cur[0]);
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
+                    for (int i = 1; i < 16; ++i) cmax = fmaxf(cmax, __uint_as_float(cur[i]));
                     // reference point in "h" units: h = acc + bias
                     const float hmax = cmax + bias_f;
                     a.mx = fmaxf(a.mx, hmax);
@@ -291,9 +298,9 @@ head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __g
                     const uint64_t l2e2 = pk2(kLog2e, kLog2e), k02 = pk2(k0, k0);
                     uint64_t s2a = pk2(0.f, 0.f), s2b = s2a, w2a = s2a, w2b = s2a;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         float t0, t1;
-                        up2(ffma2(pk2(v[2 * i], v[2 * i + 1]), l2e2, k02), t0, t1);
+                        up2(ffma2(pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), l2e2, k02), t0, t1);
                         const uint64_t pp = pk2(ex2(t0), ex2(t1));
                         if (i & 1) { s2b = fadd2(s2b, pp); w2b = ffma2(pp, pk2((float)i, (float)i), w2b); }
                         else { s2a = fadd2(s2a, pp); w2a = ffma2(pp, pk2((float)i, (float)i), w2a); }
@@ -306,8 +313,13 @@ head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __g
                     a.l += s;
                     a.sx += fmaf(x0f, s, w);
                     a.sy = fmaf(yf, s, a.sy);
+                    if (q + 1 < CW / 16) {
+                        tmem_ld16_wait(nxt);
+                        if (q + 2 == CW / 16) {         // the whole accumulator stage is in registers: hand it back to the MMA warp
+                            release_stage(as);
+                        }
+                    }
                 }
-                release_stage(as);
             }
             // ---- merge the lanes (z) and the two column halves of each joint, write coords / stats
             if (!valid) a.reset();
