@@ -52,6 +52,12 @@ def parse():
     return ap.parse_args()
 
 
+def workload_name(B, J, D, W, dtype):
+    """config.workload: the same string in both arms (the driver compares the arms on metric and config)"""
+    return ("integral-L1 soft-argmax fwd+bwd (JointLocationLoss + backward), B=%d per GPU, J=%d, D=%d, H=W=%d, %s heatmaps"
+            % (B, J, D, W, dtype))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,7 +170,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / done * (B / sample_B), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "integral-L1 soft-argmax fwd+bwd, B=%d, J=%d, D=%d, H=W=%d, fp32" % (B, J, D, W)},
+        "config": {"workload": workload_name(B, J, D, W, "f32"), "residency": "host memory (CPU arm)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -349,8 +355,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "integral-L1 soft-argmax fwd+bwd (JointLocationLoss + backward), B=%d per GPU, J=%d, D=%d, H=W=%d, %s heatmaps "
-                               "resident in HBM" % (B, J, D, W, args.dtype),
+        "config": {"workload": workload_name(B, J, D, W, args.dtype), "residency": "HBM for value / roofline, pinned host memory for e2e",
                    "l2": "inputs %d MiB + gradients %d MiB per step >> 126 MB L2; no flush needed" % (R * N * es >> 20, R * N * es >> 20),
                    "variant": ihpr_b200.get_variant(), "api": "ihpr_b200.JointLocationLoss()(heat, gt, vis, have_depth); loss.backward()  [fused_backward default: K5]"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": extra, "cpu_baseline": cpu,
