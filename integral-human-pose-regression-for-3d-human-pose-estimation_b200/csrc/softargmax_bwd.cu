@@ -192,7 +192,12 @@ static void launch_bwd_t(const BwdParams& p, bool vec_ok, int variant, int num_s
         case 13: return launch_ring<T, 16384, 6, 8, 2>(p, num_sms, s);
         case 14: return launch_ring<T, 32768, 3, 16, 2>(p, num_sms, s);
         case 1: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
-        default: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
+        default:
+            // auto: once the volumes no longer fit L2 (>= 128 MiB) the fp32 backward streams faster with direct 128-bit loads, two
+            // 512-thread CTAs per SM, than through the TMA ring (B=32 64^3: 194 vs 203 us = 6.2 vs 5.9 TB/s; D=128: 383 vs 399 us);
+            // below that, and in bf16, the ring wins (profiles/r01_kbench.txt).  Both stream 32 KiB chunks (same Geometry).
+            if (sizeof(T) == 4 && (uint64_t)p.g.R * p.g.N * sizeof(T) >= (128ull << 20)) return launch_direct<T, 512, 4, 2>(p, num_sms, s);
+            return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
     }
 }
 

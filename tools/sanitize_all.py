@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""tools/sanitize_all.py -- one small invocation of every kernel of the library, meant to run under
+`compute-sanitizer --tool memcheck` (or racecheck / synccheck) on a B200.  Prints the kernels it drove."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ihpr_b200
+from ihpr_b200._lib import lib, check
+
+dev = torch.device("cuda:0")
+g = torch.Generator(device="cpu").manual_seed(0)
+
+
+def targets(B, J, D, H, W):
+    gt = (torch.rand(B, J, 3, generator=g) * torch.tensor([W, H, D], dtype=torch.float32)).to(dev)
+    return gt, torch.ones(B, J, 1, device=dev), torch.ones(B, 1, device=dev)
+
+
+def loss_step(B, J, D, H, W, dtype, fused, variant=0):
+    ihpr_b200.set_variant(variant)
+    h = torch.randn(B, J * D, H, W, generator=g).to(dev).to(dtype).requires_grad_(True)
+    gt, vis, hd = targets(B, J, D, H, W)
+    loss = ihpr_b200.integral_l1_loss(h, gt, vis, hd, fused_backward=fused)
+    (loss * 1.25).backward()
+    torch.cuda.synchronize()
+    ihpr_b200.set_variant(0)
+    assert torch.isfinite(loss).item() and torch.isfinite(h.grad.float()).all().item()
+
+
+# K1 + K2 (ring, direct, scalar paths), fp32 and bf16
+for v in (0, 2):
+    loss_step(2, 3, 8, 16, 16, torch.float32, False, v)
+loss_step(2, 3, 8, 16, 16, torch.bfloat16, False)
+loss_step(2, 2, 3, 5, 9, torch.float32, False)                     # scalar path
+# K5 (cooperative, L2-resident) and K5c (cluster-resident), enough joint-volumes for the one-launch path
+loss_step(20, 16, 8, 16, 16, torch.float32, True)                  # 8 KiB volumes: S = 1
+loss_step(10, 18, 32, 32, 32, torch.float32, True)                 # 128 KiB volumes
+loss_step(10, 18, 32, 32, 32, torch.float32, True, variant=7)      # K5c, clusters of 2
+loss_step(4, 18, 64, 64, 64, torch.float32, True, variant=7)       # K5c, clusters of 16
+loss_step(6, 18, 64, 64, 64, torch.bfloat16, True, variant=7)      # K5c, clusters of 8
+loss_step(6, 18, 64, 64, 64, torch.float32, True)                  # K5, S = 12
+# K3 / K4 (single SM and SM pair)
+for v in (0, 5):
+    ihpr_b200.set_variant(v)
+    B, J, D, K, H, W = 3, 5, 32, 128, 32, 32
+    x = torch.randn(B, K, H, W, generator=g).to(torch.bfloat16).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wt = (torch.randn(J * D, K, 1, 1, generator=g) * 0.05).to(torch.bfloat16).to(dev).requires_grad_(True)
+    bias = (torch.randn(J * D, generator=g) * 0.5).to(dev).requires_grad_(True)
+    gt, vis, hd = targets(B, J, D, H, W)
+    loss = ihpr_b200.fused_head_integral_l1_loss(x, wt, bias, gt, vis, hd)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item() and torch.isfinite(x.grad.float()).all().item()
+ihpr_b200.set_variant(0)
+# K6: test-time post-processing
+B, J = 3, 18
+coords = torch.rand(B, J, 3, device=dev) * 64
+flipped = torch.rand(B, J, 3, device=dev) * 64
+out = ihpr_b200.coords_to_camera(coords, bbox=torch.tensor([[10., 20., 200., 220.]] * B, device=dev),
+                                 center_cam=torch.tensor([[0., 0., 5000.]] * B, device=dev), f=torch.tensor([[1145., 1143.]] * B, device=dev),
+                                 c=torch.tensor([[512., 515.]] * B, device=dev), root_idx=0, flipped_coord_out=flipped,
+                                 flip_pairs=((1, 4), (2, 5), (3, 6)))
+torch.cuda.synchronize()
+print("sanitize_all: every kernel family ran once")
