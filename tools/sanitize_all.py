@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""tools/sanitize_all.py -- one small invocation of every kernel of the library, meant to run under
-`compute-sanitizer --tool memcheck` (or racecheck / synccheck) on a B200.  Prints the kernels it drove."""
+"""tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K5, K5c with
+clusters of 2 / 8 / 16, K3 / K4 single-SM and SM-pair, K6) with finiteness checks: a quick all-kernel smoke on a B200, and the
+driver to put under `compute-sanitizer --tool memcheck|racecheck|synccheck` where the pool allows it (round 1's pool does not)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
