@@ -5,14 +5,15 @@
 // common/nets/loss.py:13-52, then autograd backward).  K5 (softargmax_fused.cu) re-reads every unit from L2 and
 // trades partials through global memory between co-resident CTAs of a cooperative launch; here
 //   * a cluster of CS CTAs owns one joint-volume at a time; CTA q of the cluster streams chunks [q*C, (q+1)*C) of it
-//     ONCE from HBM into its TMA ring (CS * C * 32 KiB = N*s, i.e. 8 CTAs x 128 KiB for a 64^3 fp32 volume),
+//     ONCE from HBM into its TMA ring (CS * C * chunk = N*s, i.e. 16 CTAs x 4 x 16 KiB for a 64^3 fp32 volume),
 //   * pass 1 runs over the chunks as they land and leaves them in the ring,
 //   * the CS partials are traded through distributed shared memory (st.shared::cluster + a remote mbarrier arrive:
 //     a few hundred cycles, no global memory, no polling, no cooperative launch),
 //   * pass 2 reads the SAME ring stages again, writes the gradient and only then hands the stages back to the producer.
-// DRAM traffic is exactly read V + write V whatever the L2 does.  The ring has C + E stages: while pass 2 of volume u
-// drains C of them, the first E chunks of volume u+1 are already in flight / being accumulated, so the exchange latency
-// of u+1 hides behind pass 2 of u and the loads never stop.
+// DRAM traffic is exactly read V + write V whatever the L2 does.  The CTA's chunks form one stream; pass 2 trails pass 1 by L >= C chunks
+// (C = chunks per slice), so L ring stages hold data between the passes, the remaining STAGES - L are loading, and the L - C chunks of
+// slack hide the exchange.  Opt-in (variant 7): on B200 it loses to K5 because clusters of 8 / 16 of these 226 KiB CTAs only fill
+// 120 / 112 of the 148 SMs and the exchange needs ~3 us of slack (profiles/r01_k5c_cluster_resident.txt).
 #include <atomic>
 #include <cstdlib>
 #include <type_traits>
