@@ -15,7 +15,10 @@
  *   - stats are (B, J, 2) fp32: {m = max_i h_i, l = sum_i exp(h_i - m)}; logsumexp = m + ln l.
  *     The backward recomputes the softmax from heat + stats; the softmax is never materialised.
  *   - the caller owns every buffer, including the workspace (size from ihpr_workspace_bytes, must be
- *     zero-filled ONCE before first use; the kernels leave its tickets zeroed again).  The ticket layout
+ *     zero-filled ONCE before first use; the kernels leave its tickets zeroed again).  The device entry points allocate
+ *     nothing, free nothing and keep no pointer after they return.  The one exception is ihpr_integral_l1_fwd_bwd_host,
+ *     which takes HOST buffers and therefore owns (and caches, per device) the device staging buffers, streams and events
+ *     it copies through; ihpr_host_release frees them.  The ticket layout
  *     depends on B*J: re-zero a workspace before reusing it with a different B*J.  A workspace must not
  *     be shared by launches that may run concurrently (one per stream).
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
@@ -24,9 +27,10 @@
  *     (thread-local).  No entry point ever falls back to a CPU implementation.
  *   - NaN policy is the reference's: a row of all -inf gives NaN, +inf or NaN inputs propagate NaN
  *     to that row's outputs.
- *   - thread-safe: no global mutable state besides an immutable per-device attribute cache; the
- *     reference calls its criterion from N Python threads, one per GPU
- *     (common/nets/balanced_parallel.py:149-173).
+ *   - thread-safe: the reference calls its criterion from N Python threads, one per GPU
+ *     (common/nets/balanced_parallel.py:149-173).  Mutable state is per thread (last error, launch count, kernel variant:
+ *     two threads may hold different variants) or guarded by a mutex (the *_host entry's per-device staging cache, the
+ *     per-device kernel-choice cache filled by the first call of ihpr_integral_l1_fwd_bwd at a new shape).
  */
 #ifndef IHPR_B200_H_
 #define IHPR_B200_H_
@@ -92,7 +96,11 @@ int ihpr_integral_l1_bwd(const void *heat, int dtype, int B, int J, int D, int H
  * the shared memory of a thread-block cluster between the two passes (exactly 2 N s of DRAM traffic, but clusters of
  * 8 / 16 CTAs leave 28 / 36 of a B200's 148 SMs idle, so it is slower and not the default).  Falls back to the
  * two-kernel sequence for small batches and for shapes only the scalar kernels handle -- same results to rounding
- * either way. */
+ * either way.  With variant 0 (auto) the choice between the one-launch form and K1 + K2 is MEASURED: the first eager call on a
+ * device at a new shape runs both forms (2 + 3 extra passes, ONE cudaEventSynchronize on the caller's stream -- the only
+ * synchronisation a device entry point ever makes) and every later call at that shape runs the faster one; a call on a stream
+ * under CUDA-graph capture never measures (it uses the one-launch form until an eager call has decided).  IHPR_CALIBRATE=0
+ * or variant 8 keep the static rule (the one-launch form whenever it applies); variant 9 forces K1 + K2. */
 int ihpr_integral_l1_fwd_bwd(const void *heat, int dtype, int B, int J, int D, int H, int W,
                              const float *gt, const float *vis, const float *have_depth,
                              float *loss, float *coords, float *stats, void *grad_heat,
@@ -188,14 +196,18 @@ int ihpr_integral_l1_fwd_bwd_host(const void *heat_host, int dtype, int B, int J
 /* Frees the device buffers / streams the *_host entry point caches for `device`. */
 int ihpr_host_release(int device);
 
-/* Tuning / introspection (does not change results beyond rounding): kernel variant 0 = auto,
+/* Tuning / introspection (does not change results beyond rounding; the setting belongs to the CALLING THREAD): kernel variant 0 = auto,
  * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads; for ihpr_integral_l1_fwd_bwd
- * 7 = cluster-resident K5c where it applies, 9 = always the two-kernel sequence; for the fused-head entries
+ * 7 = cluster-resident K5c where it applies, 8 = the one-launch form whenever it applies (no measurement), 9 = always the
+ * two-kernel sequence; for the fused-head entries
  * 5 = the SM-pair (tcgen05 cta_group::2) form of K3 / K4 (bit-identical results, slower on B200: profiles/r01_ncu_K4.txt). */
 int ihpr_set_variant(int variant);
 int ihpr_get_variant(void);
 /* Number of kernels the LAST call on this thread launched (for bench.py's gpu_launches). */
 int ihpr_last_launch_count(void);
+/* What the last ihpr_integral_l1_fwd_bwd on this thread ran: 1 = one launch (K5 / K5c), 2 = K1 then K2, 0 = nothing yet;
+ * +16 when that call was the one that measured both forms for its (device, shape). */
+int ihpr_last_path_choice(void);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ihpr_set_variant": (c_int, [c_int]),
     "ihpr_get_variant": (c_int, []),
     "ihpr_last_launch_count": (c_int, []),
+    "ihpr_last_path_choice": (c_int, []),
 }
 
 

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "../../include/ihpr_b200.h"
 #include "ihpr_common.cuh"
@@ -15,7 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-std::atomic<int> g_variant{0};
+thread_local int g_variant = 0;         // per calling thread: two threads (two GPUs under the reference's DataParallelCriterion) may hold different variants
 
 
 int fail(int code, const char* fmt, ...) {
@@ -105,7 +107,7 @@ int fwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
     if (rc) return rc;
 
     const bool v = vec_ok(heat, nullptr, dtype, D, H, W);
-    const int variant = g_variant.load(std::memory_order_relaxed);
+    const int variant = g_variant;
     ihpr::FwdParams p;
     p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
     p.heat = heat; p.coords = coords; p.stats = stats;
@@ -134,7 +136,7 @@ int bwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
     rc = check_device(heat, &num_sms);
     if (rc) return rc;
     const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
-    const int variant = g_variant.load(std::memory_order_relaxed);
+    const int variant = g_variant;
     ihpr::BwdParams p;
     p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
     p.heat = heat; p.grad_heat = grad_heat; p.coords = coords; p.stats = stats;
@@ -176,8 +178,8 @@ extern "C" {
 
 int ihpr_version(void) { return IHPR_VERSION; }
 const char* ihpr_last_error(void) { return g_err; }
-int ihpr_set_variant(int variant) { g_variant.store(variant); return IHPR_OK; }
-int ihpr_get_variant(void) { return g_variant.load(); }
+int ihpr_set_variant(int variant) { g_variant = variant; return IHPR_OK; }
+int ihpr_get_variant(void) { return g_variant; }
 int ihpr_last_launch_count(void) { return g_launches; }
 
 size_t ihpr_workspace_bytes(int B, int J, int D, int H, int W) {
@@ -208,20 +210,46 @@ int ihpr_integral_l1_bwd(const void* heat, int dtype, int B, int J, int D, int H
     return bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, grad_out, scale, grad_heat, stream);
 }
 
+// ---- ihpr_integral_l1_fwd_bwd: one launch (K5 / K5c) or two (K1 + K2), chosen per device and shape ---------------------------
+// K5 is the faster form on a healthy B200 (2 N s of DRAM traffic instead of 3 N s) but it is the more fragile one: it needs more
+// instructions per byte (a power-capped GPU clocks down and loses more), its second pass depends on the L2 holding what the
+// first pass read, and its partner CTAs wait for each other.  In the 8-GPU scaling run of round 1 one rank ran it 16 % slower
+// than the others while the two streaming kernels moved by 2 %.  So the automatic choice is MEASURED: the first call on a device
+// at a shape times both forms once on the caller's stream and remembers the faster one (per device: ranks decide independently).
+namespace {
+struct ChoiceKey {
+    int dev, dtype, B, J, D, H, W;
+    bool operator<(const ChoiceKey& o) const {
+        return std::tie(dev, dtype, B, J, D, H, W) < std::tie(o.dev, o.dtype, o.B, o.J, o.D, o.H, o.W);
+    }
+};
+std::mutex g_choice_mu;
+std::map<ChoiceKey, int> g_choice;          // 1 = one launch (K5), 2 = K1 + K2
+thread_local int g_last_choice = 0;         // what the last ihpr_integral_l1_fwd_bwd on this thread ran: 1 / 2; +16 if it calibrated
+bool calibration_enabled() {
+    static const bool on = [] { const char* e = getenv("IHPR_CALIBRATE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace
+
+extern "C" int ihpr_last_path_choice(void) { return g_last_choice; }
+
 int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, int H, int W, const float* gt, const float* vis, const float* have_depth,
                              float* loss, float* coords, float* stats, void* grad_heat, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
+    g_last_choice = 0;
     int rc = check_shape(B, J, D, H, W, dtype);
     if (rc) return rc;
     if (!heat || !gt || !vis || !have_depth || !loss || !coords || !stats || !grad_heat || !workspace)
         return fail(IHPR_EINVAL, "null argument");
     const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
-    const int variant = g_variant.load(std::memory_order_relaxed);
+    const int variant = g_variant;
     const float scale = 1.0f / (3.0f * (float)B * (float)J);
     ihpr::Geometry g = ihpr::make_geometry(B, J, D, H, W, dtype, v, 0);
     int num_sms = 0;
     rc = check_device(heat, &num_sms);
     if (rc) return rc;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const int S = v ? ihpr::fused_split(g, dtype) : 1;
     // K5c (joint-volume resident in a cluster's shared memory) is opt-in (variant 7): on B200 it is slower than K5 because
     // clusters of 8 / 16 CTAs only fill 120 / 112 of the 148 SMs (profiles/r01_k5c_cluster_resident.txt)
@@ -233,15 +261,20 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     if (CS && ncl * CS * 2 < num_sms) CS = 0;              // too few joint-volumes (or clusters) to be worth a cluster launch
     // the fused kernels want enough joint-volumes to keep every CTA group busy for a few rounds; otherwise (tiny
     // batches: everything fits in L2 anyway) or on the scalar path run K1 then K2
-    const bool fused = v && variant != 9 && (CS || (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S);
-    if (!fused) {
-        rc = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
-        if (rc) return rc;
-        rc = bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, nullptr, scale, grad_heat, stream, 1.0f, true);
-        if (rc) return rc;
+    const bool big_enough = (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S;
+    const bool fused = v && variant != 9 && (CS || big_enough);
+
+    auto run_two = [&]() -> int {
+        int r2 = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
+        if (r2) return r2;
+        r2 = bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, nullptr, scale, grad_heat, stream, 1.0f, true);
+        if (r2) return r2;
         g_launches = 2;
+        g_last_choice = 2;
         return IHPR_OK;
-    }
+    };
+    if (!fused) return run_two();
+
     const WsLayout l = ws_layout(B, J, D, H, W);
     if (workspace_bytes < l.total) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, l.total);
     if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
@@ -266,24 +299,80 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
 #else
     p.debug_no_exchange = 0;
 #endif
-    cudaError_t le = CS ? ihpr::launch_fused_cluster(p, dtype, plan, ncl, static_cast<cudaStream_t>(stream)) : cudaErrorLaunchOutOfResources;
-    if (CS && le != cudaSuccess) (void)cudaGetLastError();
-    if (le != cudaSuccess && (int64_t)B * J * S >= 2 * (int64_t)(num_sms / S) * S)
-        le = ihpr::launch_fused(p, dtype, num_sms, static_cast<cudaStream_t>(stream));
-    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
-        // the S CTAs of a joint-volume cannot be made co-resident right now (GPU shared with other work): same result
-        // from the two-kernel path (still CUDA, still this library)
-        (void)cudaGetLastError();
-        rc = fwd_common(heat, dtype, B, J, D, H, W, gt, vis, have_depth, loss, coords, stats, workspace, workspace_bytes, stream);
-        if (rc) return rc;
-        rc = bwd_common(heat, dtype, B, J, D, H, W, coords, stats, nullptr, gt, vis, have_depth, nullptr, scale, grad_heat, stream, 1.0f, true);
-        if (rc) return rc;
-        g_launches = 2;
+    // returns 0 = launched, 1 = cannot be launched now (partner CTAs cannot be made co-resident: GPU shared with other work), < 0 error
+    auto run_one = [&]() -> int {
+        cudaError_t le = CS ? ihpr::launch_fused_cluster(p, dtype, plan, ncl, cs) : cudaErrorLaunchOutOfResources;
+        if (CS && le != cudaSuccess) (void)cudaGetLastError();
+        if (le != cudaSuccess && big_enough) le = ihpr::launch_fused(p, dtype, num_sms, cs);
+        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+            (void)cudaGetLastError();
+            return 1;
+        }
+        if (le != cudaSuccess) return fail(IHPR_ECUDA, "fused launch: %s", cudaGetErrorString(le));
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return fail(IHPR_ECUDA, "fused launch: %s", cudaGetErrorString(e2));
+        g_launches = 1;
+        g_last_choice = 1;
         return IHPR_OK;
+    };
+    auto one_or_two = [&]() -> int {        // same result from the two-kernel path (still CUDA, still this library) when K5 cannot launch
+        const int r1 = run_one();
+        return r1 == 1 ? run_two() : r1;
+    };
+
+    // explicit variants (7 = K5c, tuning sweeps) and IHPR_CALIBRATE=0 keep the static rule: the one-launch form whenever it applies
+    if (variant != 0 || !calibration_enabled()) return one_or_two();
+    const ChoiceKey key{-1, dtype, B, J, D, H, W};
+    ChoiceKey k2 = key;
+    IHPR_CUDA(cudaGetDevice(&k2.dev));
+    int choice = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_choice_mu);
+        auto it = g_choice.find(k2);
+        if (it != g_choice.end()) choice = it->second;
     }
-    IHPR_CUDA(le);
-    g_launches = 1;
-    IHPR_CUDA(cudaGetLastError());
+    if (choice == 2) return run_two();
+    if (choice == 1) return one_or_two();
+    // unknown shape on this device.  Timing needs a stream synchronisation, which a stream under CUDA-graph capture forbids:
+    // then run the static rule and leave the decision to a later eager call.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    IHPR_CUDA(cudaStreamIsCapturing(cs, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return one_or_two();
+    cudaEvent_t ev[4];
+    for (auto& e : ev) IHPR_CUDA(cudaEventCreate(&e));
+    auto cleanup = [&]() { for (auto& e : ev) cudaEventDestroy(e); };
+    const int REPS = 2;
+    int r1 = run_one();                      // warm-up (also proves the cooperative launch is possible at all)
+    if (r1 < 0) { cleanup(); return r1; }
+    float t_one = 1e30f, t_two = 1e30f;
+    if (r1 == 0) {
+        cudaEventRecord(ev[0], cs);
+        for (int i = 0; i < REPS && r1 == 0; ++i) r1 = run_one();
+        cudaEventRecord(ev[1], cs);
+    }
+    rc = run_two();
+    if (rc) { cleanup(); return rc; }
+    cudaEventRecord(ev[2], cs);
+    for (int i = 0; i < REPS && !rc; ++i) rc = run_two();
+    cudaEventRecord(ev[3], cs);
+    if (rc) { cleanup(); return rc; }
+    cudaError_t se = cudaEventSynchronize(ev[3]);
+    if (se != cudaSuccess) { cleanup(); return fail(IHPR_ECUDA, "calibration: %s", cudaGetErrorString(se)); }
+    if (r1 == 0) cudaEventElapsedTime(&t_one, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_two, ev[2], ev[3]);
+    cleanup();
+    choice = (r1 == 0 && t_one < t_two) ? 1 : 2;
+    {
+        std::lock_guard<std::mutex> lock(g_choice_mu);
+        g_choice[k2] = choice;
+    }
+    // the outputs now hold the two-kernel result; when the one-launch form won, leave ITS result so that this call and
+    // every later one return the same bits
+    if (choice == 1) {
+        rc = one_or_two();
+        if (rc) return rc;
+    }
+    g_last_choice |= 16;
     return IHPR_OK;
 }
 
@@ -408,7 +497,7 @@ static int head_common(const void* x_nhwc, const void* weight, const float* bias
     int rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
     // variant 5: the SM-pair (cta_group::2) form of K3 / K4
-    const bool pairs = g_variant.load(std::memory_order_relaxed) == 5 && num_sms >= 2;
+    const bool pairs = g_variant == 5 && num_sms >= 2;
     const char* err = pairs ? ihpr::launch_head_fused_pair(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat,
                                                            dbias_part, num_sms, static_cast<cudaStream_t>(stream))
                             : ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part,
@@ -444,12 +533,13 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
     const size_t n_small = R * 3 + R + B + R * 3 + R * 2 + 2;        // gt, vis, hd, coords, stats, loss, grad_out
     const size_t ws_slice = ihpr_workspace_bytes((B + slices - 1) / slices, J, D, H, W);
     if (c.device != device) {
-        c.device = device;
-        for (auto& s : c.streams) IHPR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto& s : c.streams)
+            if (!s) IHPR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         for (int i = 0; i < 64; ++i) {
-            IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
-            IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
+            if (!c.ev_in[i]) IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+            if (!c.ev_out[i]) IHPR_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
         }
+        c.device = device;          // only a fully built context is marked usable
     }
     if (c.cap_heat < heat_bytes) {
         if (c.d_heat) cudaFree(c.d_heat);
@@ -489,11 +579,24 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
     cudaStream_t s_in = c.streams[0], s_k = c.streams[1], s_out = c.streams[2];
 
     const float scale = 1.0f / (3.0f * (float)B * (float)J);
-    const int variant = g_variant.load(std::memory_order_relaxed);
     int num_sms = 0;
     rc = check_device(c.d_heat, &num_sms);
-    if (rc) return rc;
+    if (rc) {
+        for (auto& st : c.streams) cudaStreamSynchronize(st);
+        return rc;
+    }
     int launches = 0;
+    // a failure below must not return while copies to / from the caller's buffers are still in flight
+    auto drain = [&](int code) {
+        for (auto& st : c.streams) cudaStreamSynchronize(st);
+        return code;
+    };
+#define IHPR_CUDA_DRAIN(expr)                                                                           \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return drain(fail(IHPR_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_))); \
+    } while (0)
+    int prev_Bs = -1;
     for (int i = 0; i < slices; ++i) {
         const int b0 = (int)((long long)B * i / slices), b1 = (int)((long long)B * (i + 1) / slices);
         const int Bs = b1 - b0;
@@ -502,29 +605,34 @@ int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J
         const size_t off = r0 * N * es, bytes = (size_t)Bs * J * N * es;
         char* dh = static_cast<char*>(c.d_heat) + off;
         char* dg = static_cast<char*>(c.d_grad) + off;
-        IHPR_CUDA(cudaMemcpyAsync(dh, static_cast<const char*>(heat_host) + off, bytes, cudaMemcpyHostToDevice, s_in));
-        IHPR_CUDA(cudaEventRecord(c.ev_in[i], s_in));
-        IHPR_CUDA(cudaStreamWaitEvent(s_k, c.ev_in[i], 0));
+        IHPR_CUDA_DRAIN(cudaMemcpyAsync(dh, static_cast<const char*>(heat_host) + off, bytes, cudaMemcpyHostToDevice, s_in));
+        IHPR_CUDA_DRAIN(cudaEventRecord(c.ev_in[i], s_in));
+        IHPR_CUDA_DRAIN(cudaStreamWaitEvent(s_k, c.ev_in[i], 0));
+        // the ticket layout of the workspace depends on the slice's B*J (include/ihpr_b200.h): when ragged slices change it,
+        // re-zero the workspace on the kernel stream (stream order keeps it behind the previous slice's kernels)
+        if (prev_Bs >= 0 && Bs != prev_Bs) IHPR_CUDA_DRAIN(cudaMemsetAsync(c.d_ws, 0, ws_slice, s_k));
+        prev_Bs = Bs;
         rc = ihpr_softargmax3d_fwd(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, c.d_ws, ws_slice, s_k);
-        if (rc) return rc;
+        if (rc) return drain(rc);
         ++launches;
         if (grad_heat_host) {
             rc = bwd_common(dh, dtype, Bs, J, D, H, W, d_coords + r0 * 3, d_stats + r0 * 2, nullptr, d_gt + r0 * 3, d_vis + r0, d_hd + b0, d_go, scale,
                             dg, s_k);
-            if (rc) return rc;
+            if (rc) return drain(rc);
             ++launches;
-            IHPR_CUDA(cudaEventRecord(c.ev_out[i], s_k));
-            IHPR_CUDA(cudaStreamWaitEvent(s_out, c.ev_out[i], 0));
-            IHPR_CUDA(cudaMemcpyAsync(static_cast<char*>(grad_heat_host) + off, dg, bytes, cudaMemcpyDeviceToHost, s_out));
+            IHPR_CUDA_DRAIN(cudaEventRecord(c.ev_out[i], s_k));
+            IHPR_CUDA_DRAIN(cudaStreamWaitEvent(s_out, c.ev_out[i], 0));
+            IHPR_CUDA_DRAIN(cudaMemcpyAsync(static_cast<char*>(grad_heat_host) + off, dg, bytes, cudaMemcpyDeviceToHost, s_out));
         }
     }
     loss_from_coords_kernel<<<1, 32, 0, s_k>>>(d_coords, d_gt, d_vis, d_hd, (int)R, J, d_loss);
     ++launches;
-    IHPR_CUDA(cudaGetLastError());
-    IHPR_CUDA(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, s_k));
-    if (coords_host) IHPR_CUDA(cudaMemcpyAsync(coords_host, d_coords, R * 3 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
-    IHPR_CUDA(cudaStreamSynchronize(s_k));
-    IHPR_CUDA(cudaStreamSynchronize(s_out));
+    IHPR_CUDA_DRAIN(cudaGetLastError());
+    IHPR_CUDA_DRAIN(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    if (coords_host) IHPR_CUDA_DRAIN(cudaMemcpyAsync(coords_host, d_coords, R * 3 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    IHPR_CUDA_DRAIN(cudaStreamSynchronize(s_k));
+    IHPR_CUDA_DRAIN(cudaStreamSynchronize(s_out));
+#undef IHPR_CUDA_DRAIN
     g_launches = launches;
     return IHPR_OK;
 }

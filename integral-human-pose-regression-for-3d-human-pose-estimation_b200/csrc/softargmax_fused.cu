@@ -33,16 +33,19 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 //
 // Exchange protocol (no fences, no atomics, one L2 round trip after the slowest partner): every CTA of the group
 // stores its 6-word partial as six 8-byte {value, tag} pairs into its slot of the joint-volume's exchange row; every
-// exchanger polls all S slots until each pair carries this launch's tag (an 8-byte store is single-copy atomic, so a
+// exchanger polls all S slots until each pair carries this launch's tag (one 64-bit scalar store / load per pair: single-copy atomic, so a
 // matching tag proves the value next to it).  tag = launch epoch + 1; the epoch lives in the workspace and is bumped
 // by the last CTA to finish.
+// one 64-bit scalar access each way: a .v2 access is two independent 32-bit accesses under the PTX memory model, a .b64 one is
+// single-copy atomic, so a matching tag really does vouch for the value stored with it
 __device__ __forceinline__ void st_pair(uint2* p, float v, uint32_t tag) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+    const uint64_t w = ((uint64_t)tag << 32) | (uint64_t)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ uint2 ld_pair(const uint2* p) {
-    uint2 r;
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-    return r;
+    uint64_t w;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
 
 template <typename T, int CHUNK_BYTES, int STAGES, int NCW, int DEPTH>

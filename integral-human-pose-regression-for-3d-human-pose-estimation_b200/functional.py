@@ -63,26 +63,60 @@ def _f32(t, dev, shape, name):
     return t.to(torch.float32).contiguous()
 
 
-def _fwd(heat, joint_num, targets=None):
-    """heat: contiguous cuda f32/bf16.  Returns (coords, stats, loss-or-None)."""
+_raw_stream = torch._C._cuda_getCurrentRawStream       # (device index) -> cudaStream_t of torch's current stream, no Stream object
+_ws_plan = {}       # (device index, stream, B, J, D, H, W) -> (workspace tensor, data_ptr, nbytes): the steady-state call does one dict lookup
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` without its cost when `dev` already is the current device (the usual case)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return _raw_stream(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _planned_workspace(dev, stream, B, J, D, H, W):
+    key = (dev.index, stream, B, J, D, H, W)
+    plan = _ws_plan.get(key)
+    if plan is None:
+        nbytes = lib().ihpr_workspace_bytes(B, J, D, H, W)
+        ws = _workspace(dev, stream, nbytes, B * J)
+        plan = _ws_plan[key] = (ws, ws.data_ptr(), ws.numel())
+    return plan
+
+
+def _fwd(heat, joint_num, targets=None, want_stats=True):
+    """heat: contiguous cuda f32/bf16.  Returns (coords, stats, loss-or-None).  One allocation for all the small outputs."""
     B, D, H, W = _shape(heat, joint_num)
     dev = heat.device
     L = lib()
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        nbytes = L.ihpr_workspace_bytes(B, joint_num, D, H, W)
-        ws = _workspace(dev, stream, nbytes, B * joint_num)
-        coords = torch.empty((B, joint_num, 3), dtype=torch.float32, device=dev)
-        stats = torch.empty((B, joint_num, 2), dtype=torch.float32, device=dev)
+    R = B * joint_num
+    with _on_device(dev) as stream:
+        _, ws_ptr, ws_n = _planned_workspace(dev, stream, B, joint_num, D, H, W)
+        small = torch.empty(R * 5 + 1, dtype=torch.float32, device=dev)
+        base = small.data_ptr()
+        coords = small[:R * 3].view(B, joint_num, 3)
+        stats = small[R * 3:R * 5].view(B, joint_num, 2) if want_stats else None
         if targets is None:
             check(L.ihpr_softargmax3d_fwd(heat.data_ptr(), _dtype_code(heat), B, joint_num, D, H, W,
-                                          coords.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                          base, base + R * 12 if want_stats else None, ws_ptr, ws_n, stream))
             return coords, stats, None
         gt, vis, hd = targets
-        loss = torch.empty((), dtype=torch.float32, device=dev)
+        loss = small[R * 5:].view(())
         check(L.ihpr_integral_l1_fwd(heat.data_ptr(), _dtype_code(heat), B, joint_num, D, H, W,
-                                     gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), loss.data_ptr(),
-                                     coords.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                                     gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), base + R * 20,
+                                     base, base + R * 12, ws_ptr, ws_n, stream))
         return coords, stats, loss
 
 
@@ -92,6 +126,7 @@ class _SoftArgmax3D(torch.autograd.Function):
         heat = heat.contiguous()
         coords, stats, _ = _fwd(heat, joint_num)
         ctx.joint_num = joint_num
+        ctx.variant = lib().ihpr_get_variant()          # the variant is per thread; backward runs on autograd's thread
         ctx.save_for_backward(heat, coords, stats)      # heat is the conv output autograd keeps anyway; no softmax saved
         return coords
 
@@ -102,8 +137,8 @@ class _SoftArgmax3D(torch.autograd.Function):
         B, D, H, W = _shape(heat, J)
         g = grad_coords.to(torch.float32).contiguous()
         grad_heat = torch.empty_like(heat)
-        with torch.cuda.device(heat.device):
-            stream = torch.cuda.current_stream(heat.device).cuda_stream
+        with _on_device(heat.device) as stream:
+            lib().ihpr_set_variant(ctx.variant)
             check(lib().ihpr_softargmax3d_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
                                               stats.data_ptr(), g.data_ptr(), grad_heat.data_ptr(), stream))
         return grad_heat, None
@@ -116,6 +151,7 @@ class _IntegralL1(torch.autograd.Function):
         J = gt.shape[1]
         coords, stats, loss = _fwd(heat, J, (gt, vis, hd))
         ctx.joint_num = J
+        ctx.variant = lib().ihpr_get_variant()
         ctx.save_for_backward(heat, coords, stats, gt, vis, hd)
         ctx.mark_non_differentiable(coords)
         ctx.set_materialize_grads(False)         # no zero-fill launch for the unused gradient of `coords`
@@ -130,12 +166,29 @@ class _IntegralL1(torch.autograd.Function):
         B, D, H, W = _shape(heat, J)
         go = grad_loss.to(torch.float32).contiguous()
         grad_heat = torch.empty_like(heat)
-        with torch.cuda.device(heat.device):
-            stream = torch.cuda.current_stream(heat.device).cuda_stream
+        with _on_device(heat.device) as stream:
+            lib().ihpr_set_variant(ctx.variant)
             check(lib().ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
                                              stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
                                              go.data_ptr(), grad_heat.data_ptr(), stream))
         return grad_heat, None, None, None
+
+
+def _fused_fwd_bwd(heat, gt, vis, hd):
+    """K5 through the C-ABI: (loss, coords, stats, d loss / d heat for upstream gradient 1) in one launch."""
+    J = gt.shape[1]
+    B, D, H, W = _shape(heat, J)
+    dev = heat.device
+    R = B * J
+    with _on_device(dev) as stream:
+        _, ws_ptr, ws_n = _planned_workspace(dev, stream, B, J, D, H, W)
+        small = torch.empty(R * 5 + 1, dtype=torch.float32, device=dev)
+        base = small.data_ptr()
+        grad_unit = torch.empty_like(heat)
+        check(lib().ihpr_integral_l1_fwd_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, gt.data_ptr(), vis.data_ptr(),
+                                             hd.data_ptr(), base + R * 20, base, base + R * 12,
+                                             grad_unit.data_ptr(), ws_ptr, ws_n, stream))
+    return small[R * 5:].view(()), small[:R * 3].view(B, J, 3), small[R * 3:R * 5].view(B, J, 2), grad_unit
 
 
 class _IntegralL1Fused(torch.autograd.Function):
@@ -145,19 +198,8 @@ class _IntegralL1Fused(torch.autograd.Function):
     def forward(ctx, heat, gt, vis, hd):
         heat = heat.contiguous()
         J = gt.shape[1]
-        B, D, H, W = _shape(heat, J)
-        dev = heat.device
-        L = lib()
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            ws = _workspace(dev, stream, L.ihpr_workspace_bytes(B, J, D, H, W), B * J)
-            coords = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
-            stats = torch.empty((B, J, 2), dtype=torch.float32, device=dev)
-            loss = torch.empty((), dtype=torch.float32, device=dev)
-            grad_unit = torch.empty_like(heat)
-            check(L.ihpr_integral_l1_fwd_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, gt.data_ptr(), vis.data_ptr(),
-                                             hd.data_ptr(), loss.data_ptr(), coords.data_ptr(), stats.data_ptr(),
-                                             grad_unit.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        loss, coords, stats, grad_unit = _fused_fwd_bwd(heat, gt, vis, hd)
+        ctx.variant = lib().ihpr_get_variant()
         ctx.joint_num = J
         ctx.dtype_code = _dtype_code(heat)
         ctx.grad_unit = grad_unit           # consumed (scaled in place) by the first backward
@@ -178,15 +220,14 @@ class _IntegralL1Fused(torch.autograd.Function):
             dev = grad_heat.device
             if torch.cuda.current_device() != dev.index:
                 torch.cuda.set_device(dev)
-            check(L.ihpr_scale_grad(grad_heat.data_ptr(), ctx.dtype_code, grad_heat.numel(), go.data_ptr(),
-                                    torch.cuda.current_stream(dev).cuda_stream))
+            check(L.ihpr_scale_grad(grad_heat.data_ptr(), ctx.dtype_code, grad_heat.numel(), go.data_ptr(), _raw_stream(dev.index)))
             return grad_heat, None, None, None
         heat, coords, stats, gt, vis, hd = ctx.saved_tensors
         J = ctx.joint_num
         B, D, H, W = _shape(heat, J)
-        with torch.cuda.device(heat.device):
+        with _on_device(heat.device) as stream:
             # a second backward through a retained graph: the unit gradient is gone, recompute with K2
-            stream = torch.cuda.current_stream(heat.device).cuda_stream
+            L.ihpr_set_variant(ctx.variant)
             grad_heat = torch.empty_like(heat)
             check(L.ihpr_integral_l1_bwd(heat.data_ptr(), _dtype_code(heat), B, J, D, H, W, coords.data_ptr(),
                                          stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
@@ -216,6 +257,9 @@ def soft_argmax(heatmaps, joint_num):
     _shape(heatmaps, joint_num)
     if heatmaps.shape[0] == 0:                                   # empty batch: the reference returns an empty (0, J, 3) tensor
         return heatmaps.new_zeros((0, joint_num, 3), dtype=torch.float32) + 0.0 * heatmaps.sum()
+    if not (torch.is_grad_enabled() and heatmaps.requires_grad):
+        # inference (main/test.py:53-65 runs under no_grad): no autograd node, no stats for a backward that never comes
+        return _fwd(_normalise(heatmaps.detach()).contiguous(), int(joint_num), want_stats=False)[0]
     return _SoftArgmax3D.apply(_normalise(heatmaps), int(joint_num))
 
 
@@ -250,6 +294,43 @@ def integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords
     else:
         loss, coords = _IntegralL1.apply(heat, gt, vis, hd)
     return (loss, coords) if return_coords else loss
+
+
+def integral_l1_step(heatmap_out, gt_coord, gt_vis, gt_have_depth):
+    """criterion + ``loss.backward()`` of main/train.py:67-71 as ONE call and one launch (K5): computes the loss and hands
+    ``d loss / d heat`` straight to autograd -- ``heatmap_out.backward(grad)`` for the output of a network, ``.grad`` for a leaf --
+    so the step has neither the ones-fill nor the rescale launch that ``loss.backward()`` costs.  Returns ``(loss, coords)``,
+    both detached.  Same numbers as ``integral_l1_loss(...)`` followed by ``loss.backward()``."""
+    if isinstance(heatmap_out, DeferredHeatmap):
+        loss, coords = integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords=True)
+        loss.backward()
+        return loss.detach(), coords
+    _require_cuda(heatmap_out, "heatmap_out")
+    if gt_coord.dim() != 3 or gt_coord.shape[2] != 3:
+        raise ValueError("gt_coord must be (B, J, 3), got %s" % (tuple(gt_coord.shape),))
+    B, J = gt_coord.shape[0], gt_coord.shape[1]
+    _shape(heatmap_out, J)
+    if heatmap_out.shape[0] != B or B == 0:
+        raise ValueError("batch mismatch or empty batch: heatmaps %d vs gt_coord %d" % (heatmap_out.shape[0], B))
+    if not heatmap_out.requires_grad:
+        raise IhprError("integral_l1_step needs heatmaps that require grad (use integral_l1_loss for a forward-only loss)")
+    if heatmap_out.dtype not in (torch.float32, torch.bfloat16) or not heatmap_out.is_contiguous():
+        loss, coords = integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, return_coords=True)      # cast / copy: let autograd route it
+        loss.backward()
+        return loss.detach(), coords
+    dev = heatmap_out.device
+    gt = _f32(gt_coord, dev, (B, J, 3), "gt_coord")
+    vis = _f32(gt_vis, dev, (B, J), "gt_vis")
+    hd = _f32(gt_have_depth, dev, (B, 1), "gt_have_depth")
+    loss, coords, _, grad = _fused_fwd_bwd(heatmap_out.detach(), gt, vis, hd)
+    if heatmap_out.is_leaf:
+        if heatmap_out.grad is None:
+            heatmap_out.grad = grad
+        else:
+            heatmap_out.grad += grad
+    else:
+        heatmap_out.backward(grad)
+    return loss, coords
 
 
 def integral_l1_fwd_bwd_host(heat, gt_coord, gt_vis, gt_have_depth, grad_out=1.0, want_grad=True, device=0, slices=8,
@@ -358,11 +439,13 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
                                                   coords.data_ptr(), stats.data_ptr(), gt.data_ptr(), vis.data_ptr(),
                                                   hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), db_part.data_ptr(), stream))
         # conv backward = plain library GEMMs on the gradient (no layout changes: x is NHWC, dheat is (B, M, N))
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
         xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
-        dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2)   # (B, K, H, W), channels_last strides
-        dw = torch.bmm(dheat, xn).sum(0, dtype=torch.float32).view(w_shape)
-        db = db_part.sum(dim=(0, 1))                                              # fixed-order sum of K4's per-sample partials
-        return dx.to(x_dtype), dw.to(w_dtype), db.to(b_dtype), None, None, None
+        dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2).to(x_dtype) if need_x else None
+        # per-sample products leave the GEMM in fp32 (no bf16 rounding before the batch sum), summed in sample order
+        dw = torch.bmm(dheat, xn, out_dtype=torch.float32).sum(0).view(w_shape).to(w_dtype) if need_w else None
+        db = db_part.sum(dim=(0, 1)).to(b_dtype) if need_b else None              # fixed-order sum of K4's per-sample partials
+        return dx, dw, db, None, None, None
 
 
 def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth, return_coords=False):
@@ -522,6 +605,12 @@ def flip_merge(coord_out, flipped_coord_out, width, flip_pairs):
 
 def last_launch_count():
     return lib().ihpr_last_launch_count()
+
+
+def last_path_choice():
+    """What the last ``ihpr_integral_l1_fwd_bwd`` of this thread ran: 1 = one launch (K5 / K5c), 2 = K1 + K2; +16 when that call
+    was the one that measured both forms for this (device, shape)."""
+    return lib().ihpr_last_path_choice()
 
 
 def set_variant(v):

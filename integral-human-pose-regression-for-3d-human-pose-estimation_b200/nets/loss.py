@@ -14,7 +14,7 @@ import sys
 import torch
 import torch.nn as nn
 
-from ..functional import DeferredHeatmap, integral_l1_loss
+from ..functional import DeferredHeatmap, integral_l1_loss, integral_l1_step
 from ..functional import soft_argmax as _soft_argmax
 
 
@@ -54,6 +54,15 @@ class JointLocationLoss(nn.Module):
         _assert_no_grad(gt_have_depth)
         _check_cfg(heatmap_out, joint_num)
         return integral_l1_loss(heatmap_out, gt_coord, gt_vis, gt_have_depth, fused_backward=self.fused_backward)
+
+    def forward_backward(self, heatmap_out, gt_coord, gt_vis, gt_have_depth):
+        """``loss = criterion(...); loss.backward()`` (main/train.py:67-71) as one call and ONE launch: the gradient K5 produced with
+        the loss goes straight into autograd (no ones-fill, no rescale launch).  Returns the detached loss."""
+        _assert_no_grad(gt_coord)
+        _assert_no_grad(gt_vis)
+        _assert_no_grad(gt_have_depth)
+        _check_cfg(heatmap_out, gt_coord.shape[1])
+        return integral_l1_step(heatmap_out, gt_coord, gt_vis, gt_have_depth)[0]
 
 
 class JointMSELoss(nn.Module):

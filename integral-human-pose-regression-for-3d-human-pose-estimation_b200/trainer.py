@@ -5,10 +5,13 @@ DataParallelCriterion (common/nets/balanced_parallel.py:58-183, common/base.py:6
   (no per-step broadcast), gradients are averaged with an NCCL all-reduce overlapped with backward (torch DDP);
 * the loss of a step is the mean of the per-rank means, which is what `Reduce.apply(*outputs) / len(outputs)`
   computes (balanced_parallel.py:127) and equals the global mean for equal shards;
-* Adam(lr) + MultiStepLR(lr_dec_epoch, lr_dec_factor) as in base.py:75-85 / main/config.py:35-39;
+* Adam(lr) + MultiStepLR(lr_dec_epoch, lr_dec_factor) as in base.py:75-85 / main/config.py:35-39, stepped where the reference
+  steps it (top of every epoch, main/train.py:45-46): `fit()` / `start_epoch()` / `end_epoch()`; resume = base.py:56-65,109-126;
+* inference shards the batch and gathers (B, J, 3) coordinates instead of heat-maps (`predict_sharded`, main/test.py:62-65);
 * checkpoints keep the reference's layout: {'epoch', 'network', 'optimizer', 'scheduler'} with `module.`-prefixed
   network keys (main/train.py:91-96, base.py:51-65).
 """
+import contextlib
 import os
 import types
 
@@ -18,6 +21,9 @@ from torch.nn.parallel import DistributedDataParallel as DDP
 
 DEFAULT_CFG = types.SimpleNamespace(resnet_type=50, depth_dim=64, input_shape=(256, 256), output_shape=(64, 64),
                                     lr=1e-3, lr_dec_epoch=[210, 280], lr_dec_factor=0.1, batch_size=32)
+
+
+_null = contextlib.nullcontext
 
 
 def shard_range(n, rank, world):
@@ -63,8 +69,37 @@ def stage_targets(joint_img, joint_vis, joints_have_depth, device):
     return dev[:B * J * 3].view(B, J, 3), dev[B * J * 3:B * J * 4].view(B, J, 1), dev[B * J * 4:].view(B, 1)
 
 
+def gather_coords(local_coords, group=None):
+    """All ranks' (B_r, J, 3) coordinates -> one (sum B_r, J, 3) tensor on every rank, rank order = batch order.  This is what
+    replaces the reference's gather of full (B, J*D, H, W) heat-maps onto GPU 0 (main/test.py:62-65 through
+    DataParallelModel.gather, balanced_parallel.py:96-99): 12*J bytes per sample on the wire instead of 4*J*D*H*W.
+    Shards may be ragged (the last test batch): sizes are exchanged first and shorter shards padded for the collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_coords
+    world = dist.get_world_size(group)
+    n = torch.tensor([local_coords.shape[0]], device=local_coords.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(t.item()) for t in sizes]
+    cap = max(sizes)
+    padded = local_coords.new_zeros((cap,) + tuple(local_coords.shape[1:]))
+    padded[:local_coords.shape[0]] = local_coords
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded.contiguous(), group=group)
+    return torch.cat([t[:k] for t, k in zip(out, sizes)], dim=0)
+
+
+def predict_sharded(model, input_img_local, flip_pairs=None, group=None):
+    """Multi-GPU inference of main/test.py:56-76, one process per GPU: every rank runs the network and the soft-argmax (and the
+    flip-test merge) on ITS shard of the test batch, then the (B_local, J, 3) results are all-gathered."""
+    net = model.module if isinstance(model, DDP) else model
+    with torch.no_grad():
+        coords = net.predict(input_img_local, flip_pairs=flip_pairs)
+    return gather_coords(coords, group)
+
+
 class Trainer:
-    def __init__(self, model, cfg=DEFAULT_CFG, criterion=None, device=None, autocast_dtype=None, channels_last=False):
+    def __init__(self, model, cfg=DEFAULT_CFG, criterion=None, device=None, autocast_dtype=None, channels_last=False, static_graph=True):
         self.cfg = cfg
         self.device = device if device is not None else torch.device("cpu")
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -80,16 +115,58 @@ class Trainer:
             ids = [self.device.index] if self.device.type == "cuda" else None
             # BN running statistics stay per rank, as in the reference's replicas (no SyncBN, balanced_parallel.py:16-43 is dead code)
             self.model = DDP(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=25, broadcast_buffers=False,
-                             static_graph=True)
+                             static_graph=static_graph)
         else:
             self.model = model
-        # base.py:75-77 (Adam, lr from the config); the fused multi-tensor implementation when the parameters are on a GPU
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"),
-                                          capturable=(self.device.type == "cuda"))
+        # base.py:75-77 (Adam, lr from the config); the fused multi-tensor implementation when the parameters are on a GPU.
+        # On a GPU the learning rate is a DEVICE TENSOR: MultiStepLR updates it in place (fill_), so a captured CUDA graph of the
+        # step (capture()) sees every later decay without being re-captured.
+        on_gpu = self.device.type == "cuda"
+        lr = torch.tensor(float(cfg.lr), device=self.device) if on_gpu else cfg.lr
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr, fused=on_gpu, capturable=on_gpu)
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=list(cfg.lr_dec_epoch),
                                                               gamma=cfg.lr_dec_factor)               # base.py:83-85
         self.autocast_dtype = autocast_dtype
-        self.epoch = 0
+        self.epoch = 0          # the epoch being (or about to be) trained = the reference's loop variable (main/train.py:45)
+        self._graph = None
+
+    # ---- epoch loop of main/train.py:45-96 ---------------------------------------------------------------------------
+    def current_lr(self):
+        lr = self.optimizer.param_groups[0]["lr"]
+        return float(lr.item()) if isinstance(lr, torch.Tensor) else float(lr)
+
+    def start_epoch(self):
+        """`trainer.scheduler.step()` at the top of every epoch (main/train.py:46).  The reference is pinned to PyTorch 1.0.0
+        (README.md:22-24), where MultiStepLR starts at last_epoch = -1 and that call makes last_epoch == epoch, i.e. the epoch
+        trains with lr * gamma^(milestones <= epoch).  Current PyTorch already sits at last_epoch = 0 after construction, so the
+        same trajectory is: step until last_epoch == epoch (no call for epoch 0, one call per later epoch, and the right
+        number of calls after a resume)."""
+        while self.scheduler.last_epoch < self.epoch:
+            self.scheduler.step()
+        return self.current_lr()
+
+    def end_epoch(self, model_dir=None):
+        """End of the reference's epoch body: write snapshot_{epoch}.pth.tar with 'epoch': epoch (main/train.py:91-96), then advance."""
+        if model_dir is not None:
+            self.save(model_dir)
+        self.epoch += 1
+
+    def fit(self, batches, end_epoch, model_dir=None, step_fn=None, log=None):
+        """main/train.py:45-96: for epoch in range(start_epoch, end_epoch): scheduler.step(); one pass over `batches`; snapshot.
+        `batches` is a callable epoch -> iterable of (input_img, joint_img, joint_vis, joints_have_depth) for this rank, or such
+        an iterable.  Returns the last loss of every epoch (rank-local, detached)."""
+        step_fn = step_fn or self.train_step
+        history = []
+        while self.epoch < end_epoch:
+            lr = self.start_epoch()
+            last = None
+            for batch in (batches(self.epoch) if callable(batches) else batches):
+                last = step_fn(*batch)
+            if log is not None:
+                log("Epoch %d/%d lr: %g loss_loc: %s" % (self.epoch, end_epoch, lr, "-" if last is None else "%.4f" % float(last)))
+            history.append(last)
+            self.end_epoch(model_dir)
+        return history
 
     def train_step(self, input_img, joint_img, joint_vis, joints_have_depth):
         """main/train.py:54-72 for this rank's shard.  Returns the (device) loss of this rank."""
@@ -97,14 +174,24 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         if self.channels_last:
             input_img = input_img.contiguous(memory_format=torch.channels_last)
-        target = {"coord": joint_img, "vis": joint_vis, "have_depth": joints_have_depth}
-        if self.autocast_dtype is not None:
-            with torch.autocast(device_type=self.device.type, dtype=self.autocast_dtype):
-                loss = self.model(input_img, target)
-        else:
-            loss = self.model(input_img, target)
-        loss.backward()
+        loss = self._forward_backward(self.model, input_img, joint_img, joint_vis, joints_have_depth)
         self.optimizer.step()
+        return loss
+
+    def _forward_backward(self, model, input_img, joint_img, joint_vis, joints_have_depth):
+        raw = self.raw_model
+        step = getattr(getattr(raw, "criterion", None), "forward_backward", None)
+        ctx = torch.autocast(device_type=self.device.type, dtype=self.autocast_dtype) if self.autocast_dtype is not None else _null()
+        if step is not None and not getattr(raw, "fused_head", False) and self.device.type == "cuda":
+            # main/train.py:64-71 with the stored heat-map: model -> criterion + backward in ONE launch (K5), its gradient handed
+            # straight to autograd (no ones-fill, no rescale launch)
+            with ctx:
+                heat = model(input_img)
+            return step(heat, joint_img, joint_vis, joints_have_depth)
+        target = {"coord": joint_img, "vis": joint_vis, "have_depth": joints_have_depth}
+        with ctx:
+            loss = model(input_img, target)
+        loss.backward()
         return loss.detach()
 
     # ---- whole-step CUDA graph (single GPU): ~1200 launches per step become one graph replay ------------------------
@@ -112,8 +199,13 @@ class Trainer:
         """Capture forward + loss + backward + Adam step into one CUDA graph on static input buffers (PyTorch's
         whole-network capture recipe).  The sm_100a ops are capture-safe: they only enqueue on the current stream,
         take plain device pointers and allocate nothing themselves.  Afterwards `graphed_step(batch)` copies a batch
-        into the static buffers and replays.  Not combined with DDP here."""
-        assert self.world == 1 and self.device.type == "cuda"
+        into the static buffers and replays.  The learning rate is a device tensor (see __init__), so scheduler steps after the
+        capture are seen by the replays.  Under DDP (world > 1) the bucketed NCCL all-reduces are captured with the step: PyTorch's
+        recipe asks for >= 11 eager DDP iterations on the side stream first and for the process group to have been created with
+        TORCH_NCCL_ASYNC_ERROR_HANDLING=0 (bench.py sets it before init_process_group when --cuda-graph is given)."""
+        assert self.device.type == "cuda"
+        if self.world > 1:
+            warmup = max(warmup, 11)
         self._static = [t.clone() for t in (input_img, joint_img, joint_vis, joints_have_depth)]
         if self.channels_last:
             self._static[0] = self._static[0].contiguous(memory_format=torch.channels_last)
@@ -126,14 +218,9 @@ class Trainer:
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
         self._graph = torch.cuda.CUDAGraph()
-        target = {"coord": self._static[1], "vis": self._static[2], "have_depth": self._static[3]}
+
         with torch.cuda.graph(self._graph):
-            if self.autocast_dtype is not None:
-                with torch.autocast(device_type="cuda", dtype=self.autocast_dtype):
-                    loss = self.model(self._static[0], target)
-            else:
-                loss = self.model(self._static[0], target)
-            loss.backward()
+            loss = self._forward_backward(self.model, *self._static)
             self.optimizer.step()
         self._static_loss = loss.detach()
         return self
@@ -156,13 +243,31 @@ class Trainer:
             torch.save(self.state(), os.path.join(model_dir, "snapshot_%d.pth.tar" % self.epoch))     # base.py:51-54
 
     def load(self, path, map_location=None):
+        """Resume as common/base.py:56-65 + 109-126 do: network / optimizer / scheduler states, start_epoch = ckpt['epoch'] + 1, then
+        the schedule is re-pointed at the CURRENT config (milestones, gamma) and the learning rate re-derived from it
+        (lr * gamma^(milestones <= start_epoch); the reference assigns that value to `optimizer.lr`, an attribute Adam never
+        reads -- here it reaches the parameter groups).  The next start_epoch() then steps the scheduler like any other epoch."""
         ckpt = torch.load(path, map_location=map_location or self.device)
         load_reference_network(self.raw_model, ckpt["network"])
+        lr_obj = self.optimizer.param_groups[0]["lr"]
         if "optimizer" in ckpt:
             self.optimizer.load_state_dict(ckpt["optimizer"])
         if "scheduler" in ckpt:
             self.scheduler.load_state_dict(ckpt["scheduler"])
         self.epoch = int(ckpt.get("epoch", -1)) + 1                                                  # base.py:62
+        from collections import Counter
+        self.scheduler.milestones = Counter(list(self.cfg.lr_dec_epoch))                             # base.py:115-118
+        self.scheduler.gamma = self.cfg.lr_dec_factor
+        last = self.epoch - 1               # the epoch the snapshot finished = scheduler.last_epoch at save time
+        self.scheduler.last_epoch = max(last, 0)
+        lr_now = float(self.cfg.lr) * float(self.cfg.lr_dec_factor) ** sum(1 for m in self.cfg.lr_dec_epoch if m <= max(last, 0))
+        for gr in self.optimizer.param_groups:
+            if isinstance(lr_obj, torch.Tensor):        # keep the SAME device tensor: a captured graph reads it
+                lr_obj.fill_(lr_now)
+                gr["lr"] = lr_obj
+            else:
+                gr["lr"] = lr_now
+        self.scheduler._last_lr = [self.current_lr() for _ in self.optimizer.param_groups]
         return ckpt
 
 

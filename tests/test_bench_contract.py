@@ -22,7 +22,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["metric"] == "soft-argmax fwd+bwd joint-volumes/s" and d["unit"] == "joint-volumes/s"
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference itself when baseline/_ref holds its files (build container and GPU box), the oracle port otherwise
+    sys.path.insert(0, ROOT)
+    from oracle import load_reference
+    assert d["cpu_baseline"]["kind"] == ("reference" if load_reference.installed() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
@@ -30,6 +34,17 @@ def test_reference_arm_prints_the_contract_line():
     sys.path.insert(0, ROOT)
     import bench
     assert d["config"]["workload"] == bench.workload_name(2, 3, 8, 8, "f32")
+    assert d["config"] == bench.make_config(2, 3, 8, 8, "f32")             # the CUDA arm prints exactly this dict too
+
+
+def test_reference_arm_falls_back_to_the_port_and_says_so(tmp_path, monkeypatch):
+    """without baseline/_ref the arm times the oracle port and labels the line accordingly"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import load_reference
+    monkeypatch.setattr(load_reference, "INSTALL_DIR", str(tmp_path / "nothing_here"))
+    step, kind, what = bench.load_cpu_reference()
+    assert kind == "port" and "port" in what
 
 
 def test_reference_arm_other_ranks_stay_silent():

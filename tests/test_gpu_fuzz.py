@@ -43,6 +43,8 @@ def test_random_shapes_against_oracle(chunk):
         gt, vis, hd = inputs.make_targets(B, J, D, H, W, seed=idx, vis_mode="rand", hd_mode="alt")
         l64, c64, g64 = truth.fwd_bwd_f64(heat, gt, vis, hd, grad_out=0.5)
         h = torch.from_numpy(heat).to(dev).to(dtype).requires_grad_(True)
+        # variant 8: the one-launch form (K5) whenever it applies; 0: the per-device measured choice between K5 and K1 + K2
+        ihpr_b200.set_variant(8 if idx % 2 == 0 else 0)
         loss, coords = ihpr_b200.integral_l1_loss(h, *(torch.from_numpy(a).to(dev) for a in (gt, vis, hd)), return_coords=True,
                                                   fused_backward=fused)
         (loss * 0.5).backward()
@@ -63,6 +65,7 @@ def test_random_shapes_against_oracle(chunk):
         with torch.no_grad():
             c2 = ihpr_b200.soft_argmax(h, J)
         assert float((c2 - coords).abs().max()) <= 1e-3, tag
+    ihpr_b200.set_variant(0)
 
 
 @pytest.mark.parametrize("shape", [(1, 18, 64, 64, 64), (3, 17, 64, 64, 64), (5, 7, 16, 32, 64), (40, 18, 64, 64, 64)])
@@ -75,14 +78,16 @@ def test_repeated_launches_are_bit_identical(shape):
     gen = torch.Generator(device=dev).manual_seed(5)
     h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
     gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 1, "rand", "alt"))
-    for fused in (False, True):
+    for fused in (False, True, 8):
         first = None
+        ihpr_b200.set_variant(8 if fused == 8 else 0)      # 8: K5 itself, not whatever the calibration picked
         for it in range(150 if B < 10 else 30):
             h.grad = None
-            loss, coords = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True, fused_backward=fused)
+            loss, coords = ihpr_b200.integral_l1_loss(h, gt, vis, hd, return_coords=True, fused_backward=bool(fused))
             loss.backward()
             cur = (loss.detach().clone(), coords.clone(), h.grad.clone())
             if first is None:
                 first = cur
             else:
                 assert torch.equal(cur[0], first[0]) and torch.equal(cur[1], first[1]) and torch.equal(cur[2], first[2]), (shape, fused, it)
+    ihpr_b200.set_variant(0)

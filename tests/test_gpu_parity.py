@@ -130,7 +130,7 @@ def test_oracle_seeded_shapes(shape, dist, dev):
     (40, 8, 3, 5, 12, torch.float32),          # generic (non-fast) vector path inside K5
     (40, 8, 3, 5, 9, torch.float32),           # scalar shapes: falls back to K1 + K2
 ])
-@pytest.mark.parametrize("variant", [0, 7])     # 0: the L2-resident K5; 7: the cluster-resident K5c where it applies, else K5
+@pytest.mark.parametrize("variant", [8, 7, 0])     # 8: the L2-resident K5; 7: the cluster-resident K5c where it applies, else K5; 0: measured choice
 def test_fused_forward_backward(case, variant, dev):
     import ihpr_b200
     B, J, D, H, W, dtype = case
@@ -158,6 +158,7 @@ def test_fused_is_deterministic_and_retained_graph_backward(dev):
     gen = torch.Generator(device=dev).manual_seed(3)
     h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
     gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 3, "rand", "alt"))
+    ihpr_b200.set_variant(8)            # K5 itself
     outs = []
     for _ in range(3):
         h.grad = None
@@ -549,3 +550,190 @@ def test_trainer_cuda_graph_matches_eager(dev):
     assert not torch.equal(net.head.final_layer.weight, w_before)            # Adam stepped inside the graph
     again = tr.graphed_step(*b1).item()
     assert np.isfinite(again) and again != got
+
+
+HEAD_CASES = [
+    (2, 18, 64, 64, 64, 256),       # the headline head: 1152 channels = 9 tiles of 128
+    (3, 5, 32, 32, 32, 128),
+    (2, 17, 64, 64, 64, 256),       # J = 17: 1088 channels, a partial last channel tile
+    (200, 2, 32, 8, 32, 64),        # more items than SMs
+    (1, 3, 128, 16, 32, 192),       # D = 128, K = 192
+]
+
+
+def _head_problem(case, seed_off=0):
+    B, J, D, H, W, K = case
+    g = torch.Generator(device="cpu").manual_seed(7 + B + seed_off)
+    x = torch.randn(B, K, H, W, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(J * D, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(J * D, generator=g) * 0.5
+    gt, vis, hd = (torch.from_numpy(a) for a in inputs.make_targets(B, J, D, H, W, 3, "rand", "alt"))
+    return x, wt, bias, gt, vis, hd
+
+
+def _head_truth64(x, wt, bias, gt, vis, hd, grad_out):
+    """fp64 truth of final_layer + JointLocationLoss on the bf16-rounded operands: heat-map by an fp64 GEMM, loss and d loss / d heat
+    by the oracle (truth64.c), parameter gradients by fp64 GEMMs on that gradient (conv backward, main/model.py:14-20,42)."""
+    B, K, H, W = x.shape
+    M = wt.shape[0]
+    x64 = x.double().reshape(B, K, H * W)
+    heat64 = torch.matmul(wt.double(), x64) + bias.double().view(1, M, 1)
+    heat32 = heat64.float().reshape(B, M, H, W).numpy()
+    loss, coords, dheat = truth.fwd_bwd_f64(heat32, gt.numpy(), vis.numpy(), hd.numpy(), grad_out=grad_out)
+    dh = torch.from_numpy(dheat).reshape(B, M, H * W)
+    dw = torch.einsum("bmn,bkn->mk", dh, x64)
+    dx = torch.matmul(wt.double().t(), dh).reshape(B, K, H, W)
+    db = dh.sum(dim=(0, 2))
+    return loss, coords, dh, dw, dx, db
+
+
+@pytest.mark.parametrize("case", HEAD_CASES)
+def test_fused_head_heatmap_gradient_vs_oracle(case, dev):
+    """K4 directly (ihpr_head_integral_l1_bwd through the C-ABI): the bf16 d loss / d heat-map element-wise against the fp64
+    oracle on conv(x_bf16, w_bf16) + bias, under the stated bf16 rule |a - b| <= 2^-8 |b| + 1e-4 max|b|; the
+    fp32 bias-gradient partials against the oracle's row sums."""
+    import ihpr_b200
+    from ihpr_b200._lib import lib, check
+    B, J, D, H, W, K = case
+    x, wt, bias, gt, vis, hd = _head_problem(case)
+    loss64, c64, dh64, _, _, db64 = _head_truth64(x, wt, bias, gt, vis, hd, 1.5)
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last)
+    wd, bd = wt.to(dev), bias.to(dev)
+    gtd, visd, hdd, go = gt.to(dev), vis.to(dev).reshape(B, J).contiguous(), hd.to(dev), torch.full((), 1.5, device=dev)
+    with torch.no_grad():
+        coords, stats = ihpr_b200.fused_head_soft_argmax(xd, wd, bd, J, return_stats=True)
+    dheat = torch.full((B, J * D, H * W), float("nan"), dtype=torch.bfloat16, device=dev)
+    dbp = torch.full((B, 4, J * D), float("nan"), device=dev)
+    with torch.cuda.device(dev):
+        check(lib().ihpr_head_integral_l1_bwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), B, K, J, D, H, W, coords.data_ptr(), stats.data_ptr(),
+                                              gtd.data_ptr(), visd.data_ptr(), hdd.data_ptr(), go.data_ptr(), dheat.data_ptr(), dbp.data_ptr(),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize()
+    assert coord_err(coords.cpu().numpy().astype(np.float64), c64) <= 1e-4            # K3: BASELINE.md 5 bf16-operand bound
+    got = dheat.float().cpu().double()
+    bound = 2.0 ** -8 * dh64.abs() + 1e-4 * dh64.abs().max()
+    assert not torch.isnan(got).any()
+    assert ((got - dh64).abs() <= bound).all(), float(((got - dh64).abs() - bound).max())
+    db = dbp.sum(dim=(0, 1)).cpu().double()
+    assert (db - db64).abs().max().item() <= 1e-4 * db64.abs().max().item() + 1e-7
+
+
+def test_one_launch_step_equals_criterion_plus_backward(dev):
+    """JointLocationLoss.forward_backward / integral_l1_step: the same loss and gradient bits as criterion(...) + loss.backward(),
+    with exactly one launch, for a leaf heat-map (gradient lands in .grad) and for a network output (gradient flows on)."""
+    import ihpr_b200
+    B, J, D, H, W = 10, 18, 64, 64, 64
+    gen = torch.Generator(device=dev).manual_seed(5)
+    h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
+    gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 0, "rand", "alt"))
+    crit = ihpr_b200.JointLocationLoss()
+    loss = crit(h, gt, vis, hd)
+    loss.backward()
+    g_ref, l_ref = h.grad.clone(), loss.detach().clone()
+    h.grad = None
+    l2 = crit.forward_backward(h, gt, vis, hd)
+    assert ihpr_b200.last_launch_count() == ihpr_b200.last_path_choice() & 3        # 1 launch (K5) or 2 (K1 + K2): the measured choice
+    assert torch.equal(l2, l_ref) and torch.equal(h.grad, g_ref)
+    l3 = crit.forward_backward(h, gt, vis, hd)                  # accumulates like autograd does
+    assert torch.equal(h.grad, 2 * g_ref) and torch.equal(l3, l_ref)
+    # non-leaf: the gradient is propagated to what produced the heat-map
+    w = torch.full((), 2.0, device=dev, requires_grad=True)
+    base = h.detach()
+    l4 = crit.forward_backward(base * w, gt, vis, hd)
+    loss5 = crit(base * w, gt, vis, hd)
+    (g5,) = torch.autograd.grad(loss5, w)
+    assert torch.equal(l4, loss5.detach()) and torch.allclose(w.grad, g5, rtol=1e-6, atol=0)
+
+
+def test_full_size_gradient_vs_oracle_on_samples(dev):
+    """BASELINE shape (B=32, J=18, 64^3 fp32): the GRADIENT of two whole samples element-wise against the fp64 oracle (the oracle's
+    1/(3*B*J) is rescaled to the full batch), for the one-launch path (K5) and the two-kernel path (K1 + K2)."""
+    import ihpr_b200
+    B, J, D, H, W = 32, 18, 64, 64, 64
+    gen = torch.Generator(device=dev).manual_seed(3)
+    h = torch.randn(B, J * D, H, W, device=dev, generator=gen).requires_grad_(True)
+    gt, vis, hd = (torch.from_numpy(a).to(dev) for a in inputs.make_targets(B, J, D, H, W, 0, "rand", "alt"))
+    for fused in (True, False):
+        h.grad = None
+        loss = ihpr_b200.integral_l1_loss(h, gt, vis, hd, fused_backward=fused)
+        loss.backward()
+        for b in (0, 17, B - 1):
+            hb = h.detach()[b:b + 1].cpu().numpy()
+            _, _, g64 = truth.fwd_bwd_f64(hb, gt[b:b + 1].cpu().numpy(), vis[b:b + 1].cpu().numpy(), hd[b:b + 1].cpu().numpy())
+            g64 = g64 / B
+            got = h.grad[b:b + 1].cpu().numpy().astype(np.float64)
+            assert grad_err(got, g64) <= TOL, (fused, b, grad_err(got, g64))
+
+
+def _nccl_worker(rank, world, port, out):
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, global_mean_of_rank_means, predict_sharded, shard_range, synthetic_batch
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=32, input_shape=(128, 128), output_shape=(32, 32), lr=1e-3,
+                                lr_dec_epoch=[2, 3], lr_dec_factor=0.1, batch_size=4)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3, fused_head=(out.endswith("fused")))
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.05)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 0.0
+            m.eval()
+    tr = Trainer(net, cfg, device=dev)
+    tr.model.train = lambda *a, **k: tr.model
+    img, coord, vis, hd = synthetic_batch(4, 3, cfg, dev, seed=1)
+    lo, hi = shard_range(4, rank, world)
+    loss = tr.train_step(img[lo:hi], coord[lo:hi], vis[lo:hi], hd[lo:hi])
+    g = global_mean_of_rank_means(loss)
+    net.eval()
+    coords = predict_sharded(tr.model, img[lo:hi])
+    if rank == 0:
+        torch.save({"loss": g.cpu(), "gw": tr.raw_model.head.final_layer.weight.grad.float().cpu(),
+                    "gc": tr.raw_model.backbone.conv1.weight.grad.float().cpu(), "coords": coords.cpu()}, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_two_rank_nccl_step_equals_single_process(fused, dev, tmp_path):
+    """N2 on real GPUs: two processes (one per GPU, NCCL gradient all-reduce through DDP) take the same step as one process on
+    the whole batch -- loss = mean of rank means, averaged gradients = global gradient -- and sharded inference gathers the
+    same (B, J, 3) coordinates.  Needs 2 GPUs (skipped on the 1-GPU test box; run with `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import types
+    import torch.multiprocessing as mp
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, synthetic_batch
+    out = str(tmp_path / ("r0" + ("fused" if fused else "")))
+    mp.spawn(_nccl_worker, args=(2, 29700 + os.getpid() % 2000, out), nprocs=2, join=True)
+    got = torch.load(out)
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=32, input_shape=(128, 128), output_shape=(32, 32), lr=1e-3,
+                                lr_dec_epoch=[2, 3], lr_dec_factor=0.1, batch_size=4)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3, fused_head=fused)
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.05)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 0.0
+            m.eval()
+    tr = Trainer(net, cfg, device=dev)
+    tr.model.train = lambda *a, **k: tr.model
+    img, coord, vis, hd = synthetic_batch(4, 3, cfg, dev, seed=1)
+    loss = tr.train_step(img, coord, vis, hd)
+    net.eval()
+    with torch.no_grad():
+        coords = net.predict(img)
+    tol = 2e-2 if fused else 1e-4
+    assert abs(got["loss"].item() - loss.item()) <= tol * max(1.0, abs(loss.item()))
+    for key, par in (("gw", net.head.final_layer.weight), ("gc", net.backbone.conv1.weight)):
+        ref = par.grad.float().cpu()                           # DDP leaves the rank-averaged gradient in .grad
+        assert (got[key] - ref).abs().max().item() <= (3e-2 if fused else 2e-3) * ref.abs().max().item(), key
+    assert (got["coords"] - coords.cpu()).abs().max().item() <= (0.05 if fused else 1e-3)

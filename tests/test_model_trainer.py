@@ -103,3 +103,59 @@ def test_two_rank_gloo_step_equals_single_process(built_lib, tmp_path):
     # mean of the two rank means == global mean (equal shards, balanced_parallel.py:127); averaged gradients == global gradient
     assert abs(got["loss"].item() - loss.item()) <= 1e-6
     assert torch.allclose(got["w"], net.head.final_layer.weight, atol=1e-6)
+
+
+def test_epoch_loop_steps_the_schedule_where_the_reference_does_and_resumes(built_lib, tmp_path):
+    """main/train.py:45-46 + 91-96 and common/base.py:56-65,109-126: lr * gamma^(milestones <= epoch) during epoch `epoch` (the
+    trajectory of the reference's pinned PyTorch 1.0.0), snapshot_{epoch} carries 'epoch': epoch, a resume restarts at epoch + 1 with
+    the right learning rate and keeps decaying."""
+    from oracle.soft_argmax_ref import RefJointLocationLoss
+    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.trainer import Trainer, synthetic_batch
+    cfg = tiny_cfg()                                   # lr 1e-3, milestones [2, 3], gamma 0.1
+    torch.manual_seed(0)
+    tr = Trainer(get_pose_net(cfg, True, 3), cfg, criterion=RefJointLocationLoss())
+    batch = synthetic_batch(2, 3, cfg, None, seed=1)
+    seen = []
+    hist = tr.fit(lambda epoch: [batch], end_epoch=5, model_dir=str(tmp_path), log=seen.append)
+    lrs = [float(line.split("lr: ")[1].split(" ")[0]) for line in seen]
+    assert lrs == pytest.approx([1e-3, 1e-3, 1e-4, 1e-5, 1e-5])
+    assert len(hist) == 5 and tr.epoch == 5
+    assert sorted(os.listdir(str(tmp_path))) == ["snapshot_%d.pth.tar" % e for e in range(5)]
+    assert torch.load(os.path.join(str(tmp_path), "snapshot_3.pth.tar"))["epoch"] == 3
+    # resume from the end of epoch 1: epochs 2.. continue on the same trajectory
+    tr2 = Trainer(get_pose_net(cfg, True, 3), cfg, criterion=RefJointLocationLoss())
+    tr2.load(os.path.join(str(tmp_path), "snapshot_1.pth.tar"))
+    assert tr2.epoch == 2 and tr2.current_lr() == pytest.approx(1e-3)
+    seen2 = []
+    tr2.fit([batch], end_epoch=4, log=seen2.append)
+    assert [float(line.split("lr: ")[1].split(" ")[0]) for line in seen2] == pytest.approx([1e-4, 1e-5])
+    # a resume under a changed schedule follows the CURRENT config (base.py:115-126)
+    cfg3 = tiny_cfg()
+    cfg3.lr_dec_epoch = [1, 4]
+    tr3 = Trainer(get_pose_net(cfg3, True, 3), cfg3, criterion=RefJointLocationLoss())
+    tr3.load(os.path.join(str(tmp_path), "snapshot_1.pth.tar"))
+    assert tr3.current_lr() == pytest.approx(1e-4) and tr3.start_epoch() == pytest.approx(1e-4)
+
+
+def _gather_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ihpr_b200.trainer import gather_coords, shard_range
+    full = torch.arange(5 * 3 * 3, dtype=torch.float32).view(5, 3, 3)
+    lo, hi = shard_range(5, rank, world)                     # ragged: 2 + 3 samples
+    got = gather_coords(full[lo:hi].clone())
+    torch.save(got, out + str(rank))
+    dist.destroy_process_group()
+
+
+def test_sharded_inference_gathers_coordinates_not_heatmaps(built_lib, tmp_path):
+    """main/test.py:62-65 one process per GPU: every rank keeps its shard's (B_r, J, 3) result and all-gathers it (ragged shards too)."""
+    out = str(tmp_path / "g")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_gather_worker, args=(2, port, out), nprocs=2, join=True)
+    full = torch.arange(5 * 3 * 3, dtype=torch.float32).view(5, 3, 3)
+    for r in range(2):
+        assert torch.equal(torch.load(out + str(r)), full)
