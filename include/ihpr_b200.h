@@ -175,13 +175,30 @@ int ihpr_head_softargmax_fwd(const void *x_nhwc, const void *weight, const float
  * tile by tile on the tensor cores and writes d loss / d heat-map (bf16, (B, J*D, H, W) contiguous) from the coords /
  * stats the forward produced; grad_out is the device scalar d objective / d loss.  dbias_partial (may be NULL) receives
  * (B, 4, J*D) fp32 partial sums of the unrounded gradient: d loss / d bias = their sum over the first two axes.
- * The caller turns grad_heat into dW / dX with plain GEMMs (conv backward).  Together the two entries replace final_layer + criterion +
- * loss.backward() (main/train.py:64-71) without the heat-map ever being stored. */
+ * This entry is for callers that want d loss / d heat-map itself; training uses ihpr_head_integral_l1_bwd_params below,
+ * which goes all the way to dW / dX / dbias without storing this gradient either. */
 int ihpr_head_integral_l1_bwd(const void *x_nhwc, const void *weight, const float *bias,
                               int B, int K, int J, int D, int H, int W,
                               const float *coords, const float *stats,
                               const float *gt, const float *vis, const float *have_depth,
                               const float *grad_out, void *grad_heat, float *dbias_partial, void *stream);
+
+/* The complete backward of final_layer + soft_argmax + JointLocationLoss (main/model.py:14-20,42 under main/train.py:67-71)
+ * with NOTHING heat-map-sized stored: d loss / d weight (J*D, K) fp32, d loss / d bias (J*D) fp32 and d loss / d x
+ * (B, H, W, K) bf16 -- the channels_last layout of x -- come straight out of two tensor-core kernels (csrc/head_fused_bwd.cu):
+ * each recomputes heat-map tiles in TMEM, turns them into bf16 gradient tiles in shared memory and feeds those to a second
+ * tcgen05.mma (dW: summed over pixels per channel tile, then over the batch in fixed order; dX: summed over all channel
+ * tiles per pixel tile).  No library GEMM, no atomics: results are bit-reproducible.  Any of dx_nhwc / dweight / dbias may
+ * be NULL (not needed).  coords / stats are what ihpr_head_softargmax_fwd produced; grad_out is the device scalar
+ * d objective / d loss.  workspace: ihpr_head_bwd_workspace_bytes bytes, 256-byte aligned, no initialisation needed.
+ * Same shape limits as ihpr_head_softargmax_fwd.  3-4 launches (constants, dW kernel + batch reduction, dX kernel). */
+size_t ihpr_head_bwd_workspace_bytes(int B, int K, int J, int D, int H, int W);
+int ihpr_head_integral_l1_bwd_params(const void *x_nhwc, const void *weight, const float *bias,
+                                     int B, int K, int J, int D, int H, int W,
+                                     const float *coords, const float *stats,
+                                     const float *gt, const float *vis, const float *have_depth,
+                                     const float *grad_out, void *dx_nhwc, float *dweight, float *dbias,
+                                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in

@@ -508,6 +508,45 @@ static int head_common(const void* x_nhwc, const void* weight, const float* bias
     return IHPR_OK;
 }
 
+static int head_shape_check(int B, int K, int J, int D, int H, int W) {
+    if (B <= 0 || J <= 0) return fail(IHPR_EINVAL, "non-positive dimension");
+    if (K <= 0 || K % 64 != 0 || K > 256) return fail(IHPR_EINVAL, "fused head needs K a multiple of 64, at most 256 (got %d)", K);
+    if (D != 32 && D != 64 && D != 128) return fail(IHPR_EINVAL, "fused head needs depth_dim 32, 64 or 128 (got %d)", D);
+    if (H <= 0 || W <= 0 || (H * W) % 256 != 0 || W % 32 != 0) return fail(IHPR_EINVAL, "fused head needs W %% 32 == 0 and H*W %% 256 == 0 (got %dx%d)", H, W);
+    if ((long long)B * H * W > 0x7fffffffLL) return fail(IHPR_EINVAL, "B*H*W does not fit in 31 bits");
+    return IHPR_OK;
+}
+
+size_t ihpr_head_bwd_workspace_bytes(int B, int K, int J, int D, int H, int W) {
+    if (B <= 0 || K <= 0 || J <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return ihpr::head_bwd_workspace_bytes(B, K, J, D, H, W);
+}
+
+int ihpr_head_integral_l1_bwd_params(const void* x_nhwc, const void* weight, const float* bias, int B, int K, int J, int D, int H, int W,
+                                     const float* coords, const float* stats, const float* gt, const float* vis, const float* have_depth,
+                                     const float* grad_out, void* dx_nhwc, float* dweight, float* dbias, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    g_launches = 0;
+    if (!x_nhwc || !weight || !bias || !coords || !stats || !gt || !vis || !have_depth || !grad_out || !workspace) return fail(IHPR_EINVAL, "null argument");
+    if (!dx_nhwc && !dweight && !dbias) return fail(IHPR_EINVAL, "no gradient requested");
+    int rc = head_shape_check(B, K, J, D, H, W);
+    if (rc) return rc;
+    if (((uintptr_t)x_nhwc | (uintptr_t)weight | (uintptr_t)dx_nhwc | (uintptr_t)dweight) & 15) return fail(IHPR_EINVAL, "x / weight / dx / dweight must be 16-byte aligned");
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    const size_t need = ihpr::head_bwd_workspace_bytes(B, K, J, D, H, W);
+    if (workspace_bytes < need) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, need);
+    int num_sms = 0;
+    rc = check_device(x_nhwc, &num_sms);
+    if (rc) return rc;
+    int launches = 0;
+    const char* err = ihpr::launch_head_bwd_params(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, have_depth, grad_out, dx_nhwc, dweight,
+                                                   dbias, workspace, num_sms, &launches, static_cast<cudaStream_t>(stream));
+    if (err) return fail(IHPR_ECUDA, "%s", err);
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
                                   const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
                                   int device, int slices) {

@@ -1,0 +1,553 @@
+// head_fused_bwd.cu -- K4w / K4x: the WHOLE backward of HeadNet.final_layer + soft_argmax + JointLocationLoss
+// (/root/reference/main/model.py:14-20,42 under main/train.py:67-71) on the tensor cores, with neither the heat-map nor its
+// gradient ever stored: d loss / d weight, d loss / d bias and d loss / d x leave the kernels, nothing (B, J*D, H, W)-sized exists.
+//
+// Both kernels are the same two-GEMM chain (flash-attention-backward shaped):
+//
+//   GEMM1   D1[128 x 256] = A1 . B1^T          the heat-map tile, recomputed (K = C_in <= 256), accumulator in TMEM
+//   epilogue dH = p * sum_c g_c (c(i) - coord_c)  from D1 and the (m, l, coords) the forward saved; bf16, written into a
+//           shared-memory staging buffer in the K-major SWIZZLE_128B layout of an A operand
+//   GEMM2   D2[128 x C_in] += dH . B2          accumulated in a second TMEM region over all the tiles of the work item
+//
+//   K4w (dW, dbias): rows = 128 output channels (one channel tile), D1 columns = 256 pixels;  A1 = W tile (stationary), B1 = X
+//        k-blocks (NHWC, K-major), B2 = the SAME X pixels read as an MN-major operand (N = C_in, contraction = pixels);
+//        D2 = dW[128 x C_in] summed over all pixels of the sample; per-(sample, channel tile) fp32 partials are reduced over the
+//        batch in fixed order by head_bwd_reduce_kernel (deterministic, no atomics).  Row sums of dH give dbias.
+//   K4x (dX): rows = 128 pixels, D1 columns = 256 output channels (H^T);  A1 = X tile (stationary), B1 = W k-blocks (K-major),
+//        B2 = W rows read MN-major (N = C_in, contraction = channels);  D2 = dX[128 px x C_in] summed over ALL channel tiles,
+//        converted to bf16 and stored NHWC by TMA.
+//
+// Why two kernels (5 GEMM passes with the forward's) instead of one: dW sums over pixels (channel-stationary work), dX sums over
+// channels (pixel-stationary work); one traversal keeps only one of them in TMEM (128 KB each next to the 128 KB heat-map tile),
+// and spilling the other as fp32 partials costs 128-256 KB per 50 MFLOP tile step -- more shared-memory and L2 traffic than the
+// MMA operands themselves.  Recomputing the K = 256 heat-map GEMM once more is cheaper.
+//
+// Pipeline per CTA (one per SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
+// warps 4..19 = epilogue.  TMEM: D1 = columns [0, 256), D2 = [256, 512): no room to double-buffer D1, so the two GEMMs take
+// turns on the tensor pipe instead -- the issuer's order is  GEMM1(t), GEMM2(second half of t-1), GEMM2(first half of t):
+// while the epilogue turns D1(t) into dH(t), GEMM2 of the previous tile's second half runs; the epilogue works through the
+// tile in two 128-column halves so that GEMM2 can start on the first half while the second is still being computed.
+#include "head_tc.cuh"
+
+namespace ihpr {
+namespace k4 {
+
+using namespace tc;
+
+constexpr int BM = 128;                 // rows of both accumulators (TMEM lanes)
+constexpr int BN = 256;                 // columns of the heat-map tile
+constexpr int BK = 64;                  // one SWIZZLE_128B row of bf16
+constexpr int MAXKB = 4;                // C_in <= 256
+constexpr int STAGES = 3;               // operand ring: 32 KiB stages shared by B1 k-blocks and B2 blocks
+constexpr int A_KB_BYTES = BM * BK * 2;         // 16 KiB
+constexpr int STAGE_BYTES = BN * BK * 2;        // 32 KiB
+constexpr int B2_SUB_BYTES = BK * BK * 2;       // 8 KiB: one [64 contraction rows x 64 n] box of an MN-major B2 block
+constexpr int STG_BLK_BYTES = BM * BK * 2;      // 16 KiB: staging block = 128 rows x 64 columns of dH (one A-operand k-block)
+constexpr int NBLK = BN / BK;                   // 4 staging blocks per tile
+constexpr int EPI_WARPS = 16;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t D2_COL = 256;
+
+constexpr size_t SMEM_BYTES = (size_t)MAXKB * A_KB_BYTES + (size_t)STAGES * STAGE_BYTES + (size_t)NBLK * STG_BLK_BYTES + 512;
+
+struct Params {
+    int B, K, J, D, H, W;
+    int M;                  // J * D output channels
+    int Mpad;               // M rounded up to 256: row length of k0tab
+    int Jpad;               // Mpad / D: row length of jtab
+    int KB;                 // K / 64
+    int MT;                 // ceil(M / 128)     (K4w)
+    int NT;                 // H*W / 256         (K4w: pixel tiles per item)
+    int PT;                 // H*W / 128         (K4x: items per sample)
+    int CB;                 // ceil(M / 256)     (K4x: channel blocks per item)
+    const float* k0tab;     // (B, Mpad): bias[c] * log2e - m[b, joint(c)] * log2e; -inf for c >= M (weight 0)
+    const float4* jtab;     // (B, Jpad): {gx, gy, gz, -(gx cx + gy cy + gz cz)} with g pre-divided by l; zeros for joints >= J
+    float* dw_part;         // K4w out: (B * MT, 128, K) fp32 partial d loss / d weight per (sample, channel tile)
+    float* db_part;         // K4w out: (B, 4, Mpad) fp32 partial d loss / d bias
+};
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor: 64 consecutive N (or M) elements are contiguous (128 B); LBO = byte
+// distance between consecutive 64-element blocks along N; SBO = byte distance between groups of 8 contraction rows
+// (cute::UMMA canonical layout  Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO))  in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor with a runtime N and an MN-major B operand (bit 16)
+__device__ __forceinline__ uint32_t idesc_bmn(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+constexpr uint32_t kIdesc1 = make_idesc(BM, BN);
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ldg_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+
+// DX = false: K4w (rows = channels).  DX = true: K4x (rows = pixels).
+//   map_a : stationary A1, box 64 x 128 rows        (K4w: W,  K4x: X)
+//   map_b1: GEMM1's streamed operand, box 64 x 256  (K4w: X,  K4x: W)
+//   map_b2: GEMM2's streamed operand, box 64 x 64   (K4w: X,  K4x: W)  -- the same tensor as B1, other box
+//   map_dx: K4x only: d loss / d x, (B*H*W, K) bf16, box 64 x 32 rows (one epilogue warp's slice)
+template <bool DX>
+__global__ void __launch_bounds__(32 * (4 + EPI_WARPS), 1)
+head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ CUtensorMap map_dx, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                     // [KB][128 x 64] bf16, stationary per item
+    uint8_t* sB = sA + MAXKB * A_KB_BYTES;                  // [STAGES][32 KiB]
+    uint8_t* sS = sB + STAGES * STAGE_BYTES;                // [4][128 x 64] bf16: dH of the current tile = GEMM2's A operand
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NBLK * STG_BLK_BYTES);
+    uint64_t* b_full = bars;                    // [STAGES] TMA -> MMA
+    uint64_t* b_empty = b_full + STAGES;        // [STAGES] MMA -> TMA
+    uint64_t* a_full = b_empty + STAGES;        // [1]
+    uint64_t* a_empty = a_full + 1;             // [1]
+    uint64_t* d1_full = a_empty + 1;            // [1]  MMA -> epilogue: heat-map tile complete
+    uint64_t* d1_empty = d1_full + 1;           // [1]  epilogue -> MMA: D1 is in registers (EPI_WARPS arrivals)
+    uint64_t* s_full = d1_empty + 1;            // [2]  epilogue -> MMA: staging half written (EPI_WARPS arrivals)
+    uint64_t* s_empty = s_full + 2;             // [2]  MMA -> epilogue: GEMM2 has read the staging half
+    uint64_t* d2_full = s_empty + 2;            // [1]  MMA -> epilogue: the item's D2 is complete
+    uint64_t* d2_empty = d2_full + 1;           // [1]  epilogue -> MMA: D2 drained (EPI_WARPS arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = DX ? p.B * p.PT : p.B * p.MT;
+    const int tiles = DX ? p.CB : p.NT;                 // GEMM1 tiles per item
+    const int HW = p.H * p.W;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        mbar_init(d1_full, 1); mbar_init(d1_empty, EPI_WARPS);
+        for (int h = 0; h < 2; ++h) { mbar_init(s_full + h, EPI_WARPS); mbar_init(s_empty + h, 1); }
+        mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    // live 64-column blocks of tile t (K4x: the last channel block of J*D may be partial; its missing W rows are zero-filled by TMA)
+    auto live_blocks = [&](int t) -> int {
+        if (!DX) return NBLK;
+        const int left = p.M - t * BN;
+        return left >= BN ? NBLK : (left + BK - 1) / BK;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0, n_item = 0;
+            auto load_b2 = [&](int row0) {       // one GEMM2 block: KB boxes of [64 contraction rows x 64 n], n-block kb at +kb * 8 KiB
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(b_empty + s, ph ^ 1);
+                mbar_expect_tx(b_full + s, (uint32_t)(p.KB * B2_SUB_BYTES));
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sB + s * STAGE_BYTES + kb * B2_SUB_BYTES, &map_b2, kb * BK, row0, b_full + s);
+                ++it;
+            };
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                int b, a_row, b1_row0, b2_row0;
+                if (DX) {
+                    b = item / p.PT;
+                    a_row = b * HW + (item - b * p.PT) * BM;        // this item's 128 pixels of X
+                    b1_row0 = 0;                                    // W rows of channel block t: t * 256
+                    b2_row0 = 0;
+                } else {
+                    b = item / p.MT;
+                    a_row = (item - b * p.MT) * BM;                 // this item's 128 channels of W
+                    b1_row0 = b * HW;                               // X rows of pixel tile t: b * HW + t * 256
+                    b2_row0 = b * HW;
+                }
+                mbar_wait(a_empty, (n_item & 1) ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_KB_BYTES));
+                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &map_a, kb * BK, a_row, a_full);
+                for (int t = 0; t < tiles; ++t) {
+                    for (int kb = 0; kb < p.KB; ++kb, ++it) {       // GEMM1 operand of tile t
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(b_empty + s, ph ^ 1);
+                        mbar_expect_tx(b_full + s, (uint32_t)STAGE_BYTES);
+                        tma_load_2d(sB + s * STAGE_BYTES, &map_b1, kb * BK, b1_row0 + t * BN, b_full + s);
+                    }
+                    if (t > 0) {                                    // GEMM2 operand, second half of tile t-1
+                        const int nb = live_blocks(t - 1);
+                        for (int j = 2; j < nb; ++j) load_b2(b2_row0 + (t - 1) * BN + j * BK);
+                    }
+                    const int nb = live_blocks(t);                  // GEMM2 operand, first half of tile t
+                    for (int j = 0; j < 2 && j < nb; ++j) load_b2(b2_row0 + t * BN + j * BK);
+                }
+                const int nb = live_blocks(tiles - 1);
+                for (int j = 2; j < nb; ++j) load_b2(b2_row0 + (tiles - 1) * BN + j * BK);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t it = 0, n_item = 0, tile_it = 0;
+            const uint32_t idesc2 = idesc_bmn(p.K);
+            const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + D2_COL;
+            uint32_t acc2 = 0;
+            // GEMM2 on staging blocks [j0, j1) of a tile: D2 += dH[:, 64 j .. 64 j + 63] . B2 block
+            auto gemm2 = [&](int j0, int j1) {
+                for (int j = j0; j < j1; ++j, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(b_full + s, ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sS + j * STG_BLK_BYTES), b_addr = smem_u32(sB + s * STAGE_BYTES);
+#pragma unroll
+                    for (int k16 = 0; k16 < BK / 16; ++k16) {
+                        // A: K-major, +32 B per 16 contraction columns; B: MN-major, 16 contraction rows = 2 groups of 8 = +2 KiB
+                        umma(tmem_d2, umma_desc(a_addr) + 2 * k16, umma_desc_mn(b_addr + k16 * 2048, B2_SUB_BYTES, 1024), idesc2, acc2);
+                        acc2 = 1;
+                    }
+                    tc_commit(b_empty + s);
+                }
+            };
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                mbar_wait(a_full, n_item & 1);
+                tc_fence_after();
+                acc2 = 0;
+                for (int t = 0; t < tiles; ++t, ++tile_it) {
+                    const uint32_t tp = tile_it & 1;
+                    mbar_wait(d1_empty, tp ^ 1);                // the epilogue holds the previous tile in registers
+                    tc_fence_after();
+                    for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                        mbar_wait(b_full + s, ph);
+                        tc_fence_after();
+                        const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * STAGE_BYTES));
+#pragma unroll
+                        for (int k16 = 0; k16 < BK / 16; ++k16) umma(tmem_d1, ad + 2 * k16, bd + 2 * k16, kIdesc1, (uint32_t)((kb | k16) != 0));
+                        tc_commit(b_empty + s);
+                    }
+                    tc_commit(d1_full);
+                    if (t > 0) {            // second half of the previous tile: its dH has been in the staging buffer for a while
+                        mbar_wait(s_full + 1, tp ^ 1);
+                        tc_fence_after();
+                        gemm2(2, live_blocks(t - 1));
+                        tc_commit(s_empty + 1);
+                    }
+                    if (t == 0) mbar_wait(d2_empty, (n_item & 1) ^ 1);     // the previous item's D2 has been drained (GEMM1 above overlapped the drain)
+                    mbar_wait(s_full + 0, tp);          // first half of this tile (the epilogue is working on it right now)
+                    tc_fence_after();
+                    gemm2(0, min(2, live_blocks(t)));
+                    tc_commit(s_empty + 0);
+                }
+                mbar_wait(s_full + 1, (tile_it & 1) ^ 1);       // second half of the item's last tile
+                tc_fence_after();
+                gemm2(2, live_blocks(tiles - 1));
+                tc_commit(s_empty + 1);
+                tc_commit(d2_full);                             // D2 complete: every MMA of the item has finished
+                tc_commit(a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int e = warp - 4;
+        const int qd = warp & 3;                    // TMEM lane quarter this warp may read
+        const int cg = e >> 2;                      // 32-column group within a 128-column half
+        const int row = qd * 32 + lane;             // row of the tile = TMEM lane
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const FastDiv divW = make_fastdiv((uint32_t)p.W);
+        const int sw = lane & 7;                    // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+        const int dshift = 31 - __clz(p.D);         // D is a power of two (32 / 64 / 128)
+        const uint64_t l2e2 = pk2(kLog2e, kLog2e);
+        uint32_t tile_it = 0, n_item = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+            int b;
+            // per-row constants
+            float k0_row = 0.f, gx_row = 0.f, gy_row = 0.f, tz_row = 0.f;       // K4w: this channel
+            float xf = 0.f, yf = 0.f;                                           // K4x: this pixel
+            int c_row = 0;
+            if (DX) {
+                b = item / p.PT;
+                const uint32_t pix = (uint32_t)((item - b * p.PT) * BM + row);
+                const uint32_t y = fdiv(pix, divW);
+                yf = u2f(y);
+                xf = u2f(pix - y * divW.d);
+            } else {
+                b = item / p.MT;
+                c_row = (item - b * p.MT) * BM + row;               // < Mpad: the tables are padded
+                k0_row = __ldg(p.k0tab + (size_t)b * p.Mpad + c_row);
+                const float4 jc = __ldg(p.jtab + (size_t)b * p.Jpad + (c_row >> dshift));
+                gx_row = jc.x; gy_row = jc.y;
+                tz_row = fmaf(jc.z, (float)(c_row & (p.D - 1)), jc.w);
+            }
+            float dsum = 0.f;
+            for (int t = 0; t < tiles; ++t, ++tile_it) {
+                const uint32_t tp = tile_it & 1;
+                mbar_wait(d1_full, tp);
+                tc_fence_after();
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int col0 = h * 128 + cg * 32;                     // first of this warp's 32 columns in this half
+                    float v[32];
+                    tmem_ld32(tmem_base + lane_off + (uint32_t)col0, v);
+                    if (h == 1) {                                           // D1 is in registers: GEMM1 of the next tile may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d1_empty);
+                    }
+                    uint32_t o[16];
+                    uint64_t b01, g22;          // (base, base + g) and (2 g, 2 g): the weight of column i is base + i * g
+                    uint64_t kk = 0;            // K4w: the row's exponent offset for every column
+                    const uint8_t* kp = nullptr;    // K4x: per-column exponent offsets of this run, 4 columns per 16-byte load
+                    if (DX) {
+                        const int c0 = t * BN + col0;                       // first channel of the run (one joint: D % 32 == 0)
+                        const float4 jc = __ldg(p.jtab + (size_t)b * p.Jpad + (c0 >> dshift));
+                        const float q = fmaf(jc.x, xf, fmaf(jc.y, yf, jc.w));
+                        const float z0 = (float)(c0 & (p.D - 1));
+                        b01 = pk2(fmaf(jc.z, z0, q), fmaf(jc.z, z0 + 1.f, q));
+                        g22 = pk2(2.f * jc.z, 2.f * jc.z);
+                        kp = reinterpret_cast<const uint8_t*>(p.k0tab + (size_t)b * p.Mpad + c0);
+                    } else {
+                        const uint32_t pix = (uint32_t)(t * BN + col0);     // first pixel of the run (one image row: W % 32 == 0)
+                        const uint32_t y = fdiv(pix, divW);
+                        const float base = fmaf(gy_row, u2f(y), fmaf(gx_row, u2f(pix - y * divW.d), tz_row));
+                        b01 = pk2(base, base + gx_row);
+                        g22 = pk2(2.f * gx_row, 2.f * gx_row);
+                        kk = pk2(k0_row, k0_row);
+                    }
+                    uint64_t ds2 = pk2(0.f, 0.f);
+#pragma unroll
+                    for (int i2 = 0; i2 < 8; ++i2) {
+                        uint64_t ka = kk, kb2 = kk;
+                        if (DX) {
+                            const uint4 u = ldg_u4(kp + i2 * 16);
+                            ka = pk2u(u.x, u.y);
+                            kb2 = pk2u(u.z, u.w);
+                        }
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int i = 2 * i2 + half;
+                            float t0, t1, d0, d1;
+                            up2(ffma2(pk2(v[2 * i], v[2 * i + 1]), l2e2, half ? kb2 : ka), t0, t1);
+                            const uint64_t dd = fmul2(pk2(ex2(t0), ex2(t1)), ffma2(pk2((float)i, (float)i), g22, b01));
+                            if (!DX) ds2 = fadd2(ds2, dd);
+                            up2(dd, d0, d1);
+                            o[i] = Elem<__nv_bfloat16>::pk(d0, d1);
+                        }
+                    }
+                    if (!DX) {
+                        float da, db;
+                        up2(ds2, da, db);
+                        dsum += da + db;
+                    }
+                    // GEMM2 of the tile before has read this half of the staging buffer
+                    if (lane == 0) mbar_wait(s_empty + h, tp ^ 1);
+                    __syncwarp();
+                    // 32 columns = 64 B of this row: chunks (cg & 1) * 4 + i of the 128-byte row of staging block 2 h + (cg >> 1)
+                    uint8_t* srow = sS + (2 * h + (cg >> 1)) * STG_BLK_BYTES + row * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        sts16(srow + (((((cg & 1) << 2) + i) ^ sw) << 4), make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                    fence_async_smem();             // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_full + h);
+                }
+            }
+            // ---- the item's second accumulator
+            mbar_wait(d2_full, n_item & 1);
+            tc_fence_after();
+            if (DX) {
+                // dX tile [128 px x K] -> bf16 -> staging (every GEMM2 has completed: the buffer is free) -> TMA store, NHWC
+                if (cg < p.KB) {
+                    uint8_t* srow = sS + cg * STG_BLK_BYTES + row * 128;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v[32];
+                        tmem_ld32(tmem_base + lane_off + D2_COL + (uint32_t)(cg * 64 + q * 32), v);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            sts16(srow + ((((q << 2) + i) ^ sw) << 4),
+                                  make_uint4(Elem<__nv_bfloat16>::pk(v[8 * i], v[8 * i + 1]), Elem<__nv_bfloat16>::pk(v[8 * i + 2], v[8 * i + 3]),
+                                             Elem<__nv_bfloat16>::pk(v[8 * i + 4], v[8 * i + 5]), Elem<__nv_bfloat16>::pk(v[8 * i + 6], v[8 * i + 7])));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d2_empty);
+                if (cg < p.KB) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int px_row = b * HW + (item - b * p.PT) * BM + qd * 32;
+                        tma_store_2d(&map_dx, sS + cg * STG_BLK_BYTES + qd * 32 * 128, cg * BK, px_row);
+                        tma_store_commit();
+                        tma_store_wait_read();      // the staging rows may be rewritten once the store has read them
+                    }
+                }
+                // the next item's epilogue writes other rows / blocks of the staging buffer than this warp just stored from
+                named_bar_sync(1, EPI_WARPS * 32);
+            } else {
+                // dW partial [128 channels x K] fp32 -> workspace, 256 contiguous bytes per thread and 64-column group
+                const bool warp_live = (item - b * p.MT) * BM + qd * 32 < p.M;     // 32 consecutive channels: live or dead together (M % 32 == 0)
+                if (cg < p.KB && warp_live) {
+                    float* dst = p.dw_part + ((size_t)item * BM + row) * p.K + cg * 64;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float v[32];
+                        tmem_ld32(tmem_base + lane_off + D2_COL + (uint32_t)(cg * 64 + q * 32), v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(dst + q * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d2_empty);
+                if (p.db_part && c_row < p.M) p.db_part[((size_t)b * 4 + cg) * p.Mpad + c_row] = dsum;
+            }
+        }
+        if (DX && lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+// per-(sample, joint) and per-(sample, channel) constants of the backward epilogues: one tiny launch
+__global__ void head_bwd_prep_kernel(const float* __restrict__ bias, const float* __restrict__ coords, const float* __restrict__ stats,
+                                     const float* __restrict__ gt, const float* __restrict__ vis, const float* __restrict__ have_depth,
+                                     const float* __restrict__ grad_out, float loss_scale, int B, int J, int D, int M, int Mpad, int Jpad,
+                                     float* __restrict__ k0tab, float4* __restrict__ jtab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < B * Mpad) {
+        const int b = idx / Mpad, c = idx - b * Mpad;
+        float k0 = -INFINITY;
+        if (c < M) k0 = __ldg(bias + c) * kLog2e - safe_c(__ldg(stats + 2 * ((size_t)b * J + c / D)));
+        k0tab[idx] = k0;
+    }
+    if (idx < B * Jpad) {
+        const int b = idx / Jpad, j = idx - b * Jpad;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < J) {
+            const size_t r = (size_t)b * J + j;
+            const float il = 1.0f / __ldg(stats + 2 * r + 1);
+            const float cx = __ldg(coords + 3 * r), cy = __ldg(coords + 3 * r + 1), cz = __ldg(coords + 3 * r + 2);
+            const float sc = __ldg(grad_out) * __ldg(vis + r) * loss_scale * il;
+            o.x = sc * sgn(cx - __ldg(gt + 3 * r));
+            o.y = sc * sgn(cy - __ldg(gt + 3 * r + 1));
+            o.z = sc * sgn(cz - __ldg(gt + 3 * r + 2)) * __ldg(have_depth + b);
+            o.w = -(o.x * cx + o.y * cy + o.z * cz);
+        }
+        jtab[idx] = o;
+    }
+}
+
+// dW[c, k] = sum_b part[b, tile(c), c % 128, k]  and  dbias[c] = sum_b sum_g db_part[b, g, c]   -- fixed order: bit-reproducible
+__global__ void head_bwd_reduce_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int B, int M, int Mpad, int K, int MT,
+                                       float* __restrict__ dw, float* __restrict__ dbias) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dw && idx < M * K) {
+        const int c = idx / K, k = idx - c * K;
+        const int mt = c / BM, r = c - mt * BM;
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += __ldg(dw_part + (((size_t)b * MT + mt) * BM + r) * K + k);
+        dw[idx] = s;
+    }
+    if (dbias && idx < M) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b)
+            for (int g = 0; g < 4; ++g) s += __ldg(db_part + ((size_t)b * 4 + g) * Mpad + idx);
+        dbias[idx] = s;
+    }
+}
+
+}  // namespace k4
+
+// ---- host side --------------------------------------------------------------------------------------------------
+size_t head_bwd_workspace_bytes(int B, int K, int J, int D, int H, int W) {
+    (void)H; (void)W;
+    const size_t M = (size_t)J * D, Mpad = (M + 255) / 256 * 256, Jpad = Mpad / D, MT = (M + 127) / 128;
+    size_t n = 0;
+    n += (size_t)B * Mpad * sizeof(float);              // k0tab
+    n = (n + 255) / 256 * 256;
+    n += (size_t)B * Jpad * sizeof(float4);             // jtab
+    n = (n + 255) / 256 * 256;
+    n += (size_t)B * 4 * Mpad * sizeof(float);          // db_part
+    n = (n + 255) / 256 * 256;
+    n += (size_t)B * MT * k4::BM * K * sizeof(float);   // dw_part
+    return n + 256;
+}
+
+const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, const float* coords,
+                                   const float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out,
+                                   void* dx_nhwc, float* dweight, float* dbias, void* workspace, int num_sms, int* launches, cudaStream_t s) {
+    using namespace k4;
+    Params p;
+    p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
+    p.M = J * D;
+    p.Mpad = (p.M + 255) / 256 * 256;
+    p.Jpad = p.Mpad / D;
+    p.KB = K / BK;
+    p.MT = (p.M + BM - 1) / BM;
+    p.NT = H * W / BN;
+    p.PT = H * W / BM;
+    p.CB = (p.M + BN - 1) / BN;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    size_t off = 0;
+    float* k0tab = reinterpret_cast<float*>(ws + off);
+    off = (off + (size_t)B * p.Mpad * sizeof(float) + 255) / 256 * 256;
+    float4* jtab = reinterpret_cast<float4*>(ws + off);
+    off = (off + (size_t)B * p.Jpad * sizeof(float4) + 255) / 256 * 256;
+    float* db_part = reinterpret_cast<float*>(ws + off);
+    off = (off + (size_t)B * 4 * p.Mpad * sizeof(float) + 255) / 256 * 256;
+    float* dw_part = reinterpret_cast<float*>(ws + off);
+    p.k0tab = k0tab; p.jtab = jtab; p.dw_part = dw_part; p.db_part = db_part;
+
+    const float loss_scale = 1.0f / (3.0f * (float)B * (float)J);
+    {
+        const int n = B * p.Mpad, th = 256;
+        head_bwd_prep_kernel<<<(n + th - 1) / th, th, 0, s>>>(bias, coords, stats, gt, vis, have_depth, grad_out, loss_scale, B, J, D, p.M, p.Mpad, p.Jpad,
+                                                              k0tab, jtab);
+        ++*launches;
+    }
+    CUtensorMap map_w128, map_w256, map_w64, map_x128, map_x256, map_x64, map_dx;
+    memset(&map_dx, 0, sizeof(map_dx));
+    const uint64_t xrows = (uint64_t)B * H * W;
+    if (!tc::make_map(&map_w128, w, (uint64_t)p.M, (uint64_t)K, 128) || !tc::make_map(&map_w256, w, (uint64_t)p.M, (uint64_t)K, 256) ||
+        !tc::make_map(&map_w64, w, (uint64_t)p.M, (uint64_t)K, 64))
+        return "cuTensorMapEncodeTiled failed for the weight";
+    if (!tc::make_map(&map_x128, x_nhwc, xrows, (uint64_t)K, 128) || !tc::make_map(&map_x256, x_nhwc, xrows, (uint64_t)K, 256) ||
+        !tc::make_map(&map_x64, x_nhwc, xrows, (uint64_t)K, 64))
+        return "cuTensorMapEncodeTiled failed for the activations";
+    if (dx_nhwc && !tc::make_map(&map_dx, dx_nhwc, xrows, (uint64_t)K, 32)) return "cuTensorMapEncodeTiled failed for d loss / d x";
+    const size_t smem = SMEM_BYTES + 1024;
+    if (dweight || dbias) {
+        auto kern = head_bwd_kernel<false>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (K4w)";
+        int grid = B * p.MT;
+        if (grid > num_sms) grid = num_sms;
+        kern<<<grid, 32 * (4 + EPI_WARPS), smem, s>>>(map_w128, map_x256, map_x64, map_dx, p);
+        ++*launches;
+        const int n = p.M * K, th = 256;
+        head_bwd_reduce_kernel<<<(n + th - 1) / th, th, 0, s>>>(dw_part, db_part, B, p.M, p.Mpad, K, p.MT, dweight, dbias);
+        ++*launches;
+    }
+    if (dx_nhwc) {
+        auto kern = head_bwd_kernel<true>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (K4x)";
+        int grid = B * p.PT;
+        if (grid > num_sms) grid = num_sms;
+        kern<<<grid, 32 * (4 + EPI_WARPS), smem, s>>>(map_x128, map_w256, map_w64, map_dx, p);
+        ++*launches;
+    }
+    return nullptr;
+}
+
+}  // namespace ihpr

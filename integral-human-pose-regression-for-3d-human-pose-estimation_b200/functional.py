@@ -394,7 +394,8 @@ def fused_head_soft_argmax(x, weight, bias, joint_num, return_stats=False):
 
 
 class _FusedHeadIntegralL1(torch.autograd.Function):
-    """final_layer (1x1 conv) + soft-argmax + L1 loss with the heat-map living only in TMEM (K3 forward, K4 backward).
+    """final_layer (1x1 conv) + soft-argmax + L1 loss with the heat-map living only in TMEM: K3 forward; K4w / K4x backward
+    (dW, dbias, dX in-kernel -- no heat-map gradient in HBM, no library GEMM).
     Saved for backward: the bf16 activations / weight and 5 floats per joint -- no heat-map, no softmax."""
 
     @staticmethod
@@ -415,6 +416,7 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=dev)
             check(lib().ihpr_integral_l1_from_coords(coords.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), B, J, loss.data_ptr(), stream))
         ctx.save_for_backward(xb, wb, bf, coords, stats, gt, vis, hd)
+        ctx.variant = lib().ihpr_get_variant()
         ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape))
         ctx.mark_non_differentiable(coords)
         ctx.set_materialize_grads(False)
@@ -431,26 +433,46 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         N = H * W
         go = grad_loss.to(torch.float32).contiguous()
         dev = xb.device
-        dheat = torch.empty((B, M, N), dtype=torch.bfloat16, device=dev)        # d loss / d heat-map, (B, J*D, H, W) layout
-        db_part = torch.empty((B, 4, M), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            check(lib().ihpr_head_integral_l1_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        L = lib()
+        if ctx.variant == 6:
+            # comparison arm only (ihpr_set_variant(6)): K4 writes the bf16 heat-map gradient and library GEMMs turn it into dX / dW
+            dheat = torch.empty((B, M, N), dtype=torch.bfloat16, device=dev)        # d loss / d heat-map, (B, J*D, H, W) layout
+            db_part = torch.empty((B, 4, M), dtype=torch.float32, device=dev)
+            with _on_device(dev) as stream:
+                check(L.ihpr_head_integral_l1_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
                                                   coords.data_ptr(), stats.data_ptr(), gt.data_ptr(), vis.data_ptr(),
                                                   hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), db_part.data_ptr(), stream))
-        # conv backward = plain library GEMMs on the gradient (no layout changes: x is NHWC, dheat is (B, M, N))
-        need_x, need_w, need_b = ctx.needs_input_grad[:3]
-        xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
-        dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2).to(x_dtype) if need_x else None
-        # per-sample products leave the GEMM in fp32 (no bf16 rounding before the batch sum), summed in sample order
-        dw = torch.bmm(dheat, xn, out_dtype=torch.float32).sum(0).view(w_shape).to(w_dtype) if need_w else None
-        db = db_part.sum(dim=(0, 1)).to(b_dtype) if need_b else None              # fixed-order sum of K4's per-sample partials
+            xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
+            dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2).to(x_dtype) if need_x else None
+            dw = torch.bmm(dheat, xn, out_dtype=torch.float32).sum(0).view(w_shape).to(w_dtype) if need_w else None
+            db = db_part.sum(dim=(0, 1)).to(b_dtype) if need_b else None
+            return dx, dw, db, None, None, None
+        # K4w / K4x: dW, dbias and dX straight out of the tensor-core kernels; neither the heat-map nor its gradient is ever stored
+        dx = torch.empty((B, H, W, K), dtype=torch.bfloat16, device=dev) if need_x else None       # = (B, K, H, W) channels_last
+        dw = torch.empty((M, K), dtype=torch.float32, device=dev) if need_w else None
+        db = torch.empty((M,), dtype=torch.float32, device=dev) if need_b else None
+        if not (need_x or need_w or need_b):
+            return None, None, None, None, None, None
+        nbytes = L.ihpr_head_bwd_workspace_bytes(B, K, J, M // J, H, W)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ptr = lambda t: t.data_ptr() if t is not None else None     # noqa: E731
+        with _on_device(dev) as stream:
+            check(L.ihpr_head_integral_l1_bwd_params(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), B, K, J, M // J, H, W,
+                                                     coords.data_ptr(), stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(),
+                                                     go.data_ptr(), ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), nbytes, stream))
+        if dx is not None:
+            dx = dx.permute(0, 3, 1, 2).to(x_dtype)                   # logical (B, K, H, W), channels_last strides, no copy for bf16 x
+        if dw is not None:
+            dw = dw.view(w_shape).to(w_dtype)
+        if db is not None:
+            db = db.to(b_dtype)
         return dx, dw, db, None, None, None
 
 
 def fused_head_integral_l1_loss(x, weight, bias, gt_coord, gt_vis, gt_have_depth, return_coords=False):
     """JointLocationLoss(final_layer(x), ...) for training without ever storing the (B, J*D, H, W) heat-map:
-    main/model.py:42 + main/train.py:67-71 as two tensor-core launches (K3, K4) plus library GEMMs for dW / dX."""
+    main/model.py:42 + main/train.py:67-71 as tensor-core launches only (K3 forward; K4w + K4x backward: dW / dbias / dX in-kernel)."""
     _require_cuda(x, "x")
     if x.dim() != 4:
         raise ValueError("x must be (B, K, H, W), got %s" % (tuple(x.shape),))

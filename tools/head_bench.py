@@ -56,9 +56,35 @@ stream = torch.cuda.current_stream().cuda_stream
 t_k4 = timeit(lambda: check(lib().ihpr_head_integral_l1_bwd(x.data_ptr(), wb.data_ptr(), bias.data_ptr(), B, K, J, D, H, W, coords.data_ptr(),
                                                             stats.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), go.data_ptr(),
                                                             dheat.data_ptr(), None, stream)))
+# K4w / K4x: dW, dbias, dX in-kernel (no heat-map gradient in HBM, no library GEMM), and the library-GEMM comparison arm on K4's output
+L = lib()
+nbytes = L.ihpr_head_bwd_workspace_bytes(B, K, J, D, H, W)
+ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+dx = torch.empty(B, H, W, K, dtype=torch.bfloat16, device=dev)
+dw = torch.empty(J * D, K, device=dev)
+db = torch.empty(J * D, device=dev)
+
+
+def params(dxp, dwp, dbp):
+    check(L.ihpr_head_integral_l1_bwd_params(x.data_ptr(), wb.data_ptr(), bias.data_ptr(), B, K, J, D, H, W, coords.data_ptr(), stats.data_ptr(),
+                                             gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), go.data_ptr(), dxp, dwp, dbp, ws.data_ptr(), nbytes, stream))
+
+
+t_k4w = timeit(lambda: params(None, dw.data_ptr(), db.data_ptr()))
+t_k4x = timeit(lambda: params(dx.data_ptr(), None, None))
+t_k4wx = timeit(lambda: params(dx.data_ptr(), dw.data_ptr(), db.data_ptr()))
+xn = x.permute(0, 2, 3, 1).reshape(B, H * W, K)
+with torch.no_grad():
+    t_lib_dx = timeit(lambda: torch.matmul(dheat.transpose(1, 2), wb))
+    t_lib_dw = timeit(lambda: torch.bmm(dheat, xn, out_dtype=torch.float32).sum(0))
 with torch.no_grad():
     c2 = ihpr_b200.soft_argmax(conv(x).float(), J)
 flop = 2.0 * B * J * D * K * H * W
+print(json.dumps({"B": B, "k4w_dW_us": round(t_k4w, 1), "k4w_TFLOPs_2gemm": round(2 * flop / t_k4w / 1e6, 1), "k4x_dX_us": round(t_k4x, 1),
+                  "k4x_TFLOPs_2gemm": round(2 * flop / t_k4x / 1e6, 1), "k4w_plus_k4x_us": round(t_k4wx, 1),
+                  "algorithmic_TFLOPs_dW_dX_only": round(2 * flop / t_k4wx / 1e6, 1), "executed_TFLOPs_4gemm": round(4 * flop / t_k4wx / 1e6, 1),
+                  "comparison_arm": {"k4_grad_heat_us": round(t_k4, 1), "library_dx_us": round(t_lib_dx, 1), "library_dw_us": round(t_lib_dw, 1),
+                                     "total_us": round(t_k4 + t_lib_dx + t_lib_dw, 1)}}))
 print(json.dumps({"variant": a.variant, "B": B, "J": J, "D": D, "K": K, "HW": H, "fused_us": round(t_fused, 1), "fused_TFLOPs": round(flop / t_fused / 1e6, 1),
                   "k4_bwd_us": round(t_k4, 1), "k4_TFLOPs": round(flop / t_k4 / 1e6, 1), "k4_write_GBps": round(B * J * D * H * W * 2 / t_k4 / 1e3, 1),
                   "conv_us": round(t_conv, 1), "k1_bf16_us": round(t_k1, 1), "conv_plus_k1_us": round(t_unf, 1),
