@@ -24,9 +24,17 @@
 //
 // Pipeline per CTA (one per SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
 // warps 4..19 = epilogue.  TMEM: D1 = columns [0, 256), D2 = [256, 512): no room to double-buffer D1, so the two GEMMs take
-// turns on the tensor pipe instead -- the issuer's order is  GEMM1(t), GEMM2(second half of t-1), GEMM2(first half of t):
-// while the epilogue turns D1(t) into dH(t), GEMM2 of the previous tile's second half runs; the epilogue works through the
-// tile in two 128-column halves so that GEMM2 can start on the first half while the second is still being computed.
+// turns on the tensor pipe instead.  The epilogue works through a tile in four 64-column steps (one staging block = one GEMM2
+// k-block each, all 16 warps on 16 columns apiece).  It pulls the WHOLE of D1 into registers during its first step (three
+// 16-column buffers per thread) and releases D1 at once, so GEMM1 of the next tile runs underneath the rest of the epilogue;
+// every staged block is handed to the issuer as soon as it is written.  The issuer's order per tile t is
+//     GEMM1(t+1), GEMM2(blocks 0..3 of t)
+// i.e. GEMM2 lags one tile behind: the tensor pipe works on GEMM1(t+1) while the epilogue of tile t fills the four staging blocks
+// (64 KiB: the whole bf16 gradient tile), then on GEMM2(t) while the epilogue of tile t+1 runs -- the per-tile period approaches
+// max(epilogue, GEMM1 + GEMM2) instead of their sum.  (A clock64 trace of the first versions, profiles/r02_k4_trace.txt: 6600-6800 clk
+// per tile against 4096 clk of MMA work -- with two staging blocks the epilogue waited on GEMM2 and GEMM2 on the epilogue in turn.)
+// The stationary operand A1 is handed over per k-block: its slot is reloaded for the next item (by warp 3) as soon as the last
+// tile's GEMM1 has read that k-block, not at the end of the item.
 #include "head_tc.cuh"
 
 namespace ihpr {
@@ -38,7 +46,8 @@ constexpr int BM = 128;                 // rows of both accumulators (TMEM lanes
 constexpr int BN = 256;                 // columns of the heat-map tile
 constexpr int BK = 64;                  // one SWIZZLE_128B row of bf16
 constexpr int MAXKB = 4;                // C_in <= 256
-constexpr int STAGES = 3;               // operand ring: 32 KiB stages shared by B1 k-blocks and B2 blocks
+constexpr int STAGES = 3;               // operand ring: 32 KiB stages shared by B1 k-blocks and B2 blocks, strictly FIFO in the issuer's order
+constexpr int NSTG = 4;                 // staging blocks: the whole bf16 gradient tile (64 KiB) -- GEMM2 of tile t runs AFTER GEMM1 of tile t+1
 constexpr int A_KB_BYTES = BM * BK * 2;         // 16 KiB
 constexpr int STAGE_BYTES = BN * BK * 2;        // 32 KiB
 constexpr int B2_SUB_BYTES = BK * BK * 2;       // 8 KiB: one [64 contraction rows x 64 n] box of an MN-major B2 block
@@ -48,7 +57,7 @@ constexpr int EPI_WARPS = 16;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D2_COL = 256;
 
-constexpr size_t SMEM_BYTES = (size_t)MAXKB * A_KB_BYTES + (size_t)STAGES * STAGE_BYTES + (size_t)NBLK * STG_BLK_BYTES + 512;
+constexpr size_t SMEM_BYTES = (size_t)MAXKB * A_KB_BYTES + (size_t)STAGES * STAGE_BYTES + (size_t)NSTG * STG_BLK_BYTES + 512;
 
 struct Params {
     int B, K, J, D, H, W;
@@ -64,7 +73,16 @@ struct Params {
     const float4* jtab;     // (B, Jpad): {gx, gy, gz, -(gx cx + gy cy + gz cz)} with g pre-divided by l; zeros for joints >= J
     float* dw_part;         // K4w out: (B * MT, 128, K) fp32 partial d loss / d weight per (sample, channel tile)
     float* db_part;         // K4w out: (B, 4, Mpad) fp32 partial d loss / d bias
+    int dbg;                // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_K4_DEBUG): 1 = no GEMM2 operand loads, 2 = no epilogue math,
+                            // 4 = no GEMM1 operand loads, 8 = no GEMM2 MMAs -- WRONG results, timing experiments only
+    long long* trace;       // same builds (IHPR_K4_TRACE=1): clock64 stamps of CTA 0, 16 slots per tile: 0-4 issuer, 8-14 epilogue warp 0
 };
+
+#ifdef IHPR_TIMING_EXPERIMENTS
+#define K4_STAMP(tile, slot) do { if (p.trace && blockIdx.x == 0 && (tile) < 64) p.trace[(tile) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define K4_STAMP(tile, slot) do { } while (0)
+#endif
 
 // MN-major SWIZZLE_128B shared-memory matrix descriptor: 64 consecutive N (or M) elements are contiguous (128 B); LBO = byte
 // distance between consecutive 64-element blocks along N; SBO = byte distance between groups of 8 contraction rows
@@ -105,17 +123,17 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                     // [KB][128 x 64] bf16, stationary per item
     uint8_t* sB = sA + MAXKB * A_KB_BYTES;                  // [STAGES][32 KiB]
-    uint8_t* sS = sB + STAGES * STAGE_BYTES;                // [4][128 x 64] bf16: dH of the current tile = GEMM2's A operand
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NBLK * STG_BLK_BYTES);
+    uint8_t* sS = sB + STAGES * STAGE_BYTES;                // [4][128 x 64] bf16: dH of one tile = GEMM2's A operand, one k-block per staging block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSTG * STG_BLK_BYTES);
     uint64_t* b_full = bars;                    // [STAGES] TMA -> MMA
     uint64_t* b_empty = b_full + STAGES;        // [STAGES] MMA -> TMA
-    uint64_t* a_full = b_empty + STAGES;        // [1]
-    uint64_t* a_empty = a_full + 1;             // [1]
-    uint64_t* d1_full = a_empty + 1;            // [1]  MMA -> epilogue: heat-map tile complete
+    uint64_t* a_full = b_empty + STAGES;        // [MAXKB] A1 k-block landed
+    uint64_t* a_empty = a_full + MAXKB;         // [MAXKB] the item's last GEMM1 has read A1 k-block kb
+    uint64_t* d1_full = a_empty + MAXKB;        // [1]  MMA -> epilogue: heat-map tile complete
     uint64_t* d1_empty = d1_full + 1;           // [1]  epilogue -> MMA: D1 is in registers (EPI_WARPS arrivals)
-    uint64_t* s_full = d1_empty + 1;            // [2]  epilogue -> MMA: staging half written (EPI_WARPS arrivals)
-    uint64_t* s_empty = s_full + 2;             // [2]  MMA -> epilogue: GEMM2 has read the staging half
-    uint64_t* d2_full = s_empty + 2;            // [1]  MMA -> epilogue: the item's D2 is complete
+    uint64_t* s_full = d1_empty + 1;            // [4]  epilogue -> MMA: staging block written (EPI_WARPS arrivals); one phase per tile
+    uint64_t* s_empty = s_full + NSTG;          // [4]  MMA -> epilogue: GEMM2 has read the staging block
+    uint64_t* d2_full = s_empty + NSTG;         // [1]  MMA -> epilogue: the item's D2 is complete
     uint64_t* d2_empty = d2_full + 1;           // [1]  epilogue -> MMA: D2 drained (EPI_WARPS arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
 
@@ -126,9 +144,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int kb = 0; kb < MAXKB; ++kb) { mbar_init(a_full + kb, 1); mbar_init(a_empty + kb, 1); }
         mbar_init(d1_full, 1); mbar_init(d1_empty, EPI_WARPS);
-        for (int h = 0; h < 2; ++h) { mbar_init(s_full + h, EPI_WARPS); mbar_init(s_empty + h, 1); }
+        for (int u = 0; u < NSTG; ++u) { mbar_init(s_full + u, EPI_WARPS); mbar_init(s_empty + u, 1); }
         mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
         mbar_fence_init();
     }
@@ -155,42 +173,53 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             auto load_b2 = [&](int row0) {       // one GEMM2 block: KB boxes of [64 contraction rows x 64 n], n-block kb at +kb * 8 KiB
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(b_empty + s, ph ^ 1);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                if (p.dbg & 1) { mbar_arrive(b_full + s); ++it; return; }
+#endif
                 mbar_expect_tx(b_full + s, (uint32_t)(p.KB * B2_SUB_BYTES));
                 for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sB + s * STAGE_BYTES + kb * B2_SUB_BYTES, &map_b2, kb * BK, row0, b_full + s);
                 ++it;
             };
+            auto load_b1 = [&](int row0) {       // GEMM1 operand of one tile: KB stages of [256 rows x 64 k]
+                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(b_empty + s, ph ^ 1);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                    if (p.dbg & 4) { mbar_arrive(b_full + s); continue; }
+#endif
+                    mbar_expect_tx(b_full + s, (uint32_t)STAGE_BYTES);
+                    tma_load_2d(sB + s * STAGE_BYTES, &map_b1, kb * BK, row0, b_full + s);
+                }
+            };
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-                int b, a_row, b1_row0, b2_row0;
-                if (DX) {
-                    b = item / p.PT;
-                    a_row = b * HW + (item - b * p.PT) * BM;        // this item's 128 pixels of X
-                    b1_row0 = 0;                                    // W rows of channel block t: t * 256
-                    b2_row0 = 0;
-                } else {
-                    b = item / p.MT;
-                    a_row = (item - b * p.MT) * BM;                 // this item's 128 channels of W
-                    b1_row0 = b * HW;                               // X rows of pixel tile t: b * HW + t * 256
-                    b2_row0 = b * HW;
-                }
-                mbar_wait(a_empty, (n_item & 1) ^ 1);
-                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_KB_BYTES));
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &map_a, kb * BK, a_row, a_full);
+                // K4x: W rows of channel block t are t * 256; K4w: X rows of pixel tile t are b * HW + t * 256
+                const int row0 = DX ? 0 : (item / p.MT) * HW;
+                // the issuer's order: GEMM1(0); per tile t: GEMM1(t+1), then GEMM2 blocks 0..3 of t
+                load_b1(row0);
                 for (int t = 0; t < tiles; ++t) {
-                    for (int kb = 0; kb < p.KB; ++kb, ++it) {       // GEMM1 operand of tile t
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(b_empty + s, ph ^ 1);
-                        mbar_expect_tx(b_full + s, (uint32_t)STAGE_BYTES);
-                        tma_load_2d(sB + s * STAGE_BYTES, &map_b1, kb * BK, b1_row0 + t * BN, b_full + s);
-                    }
-                    if (t > 0) {                                    // GEMM2 operand, second half of tile t-1
-                        const int nb = live_blocks(t - 1);
-                        for (int j = 2; j < nb; ++j) load_b2(b2_row0 + (t - 1) * BN + j * BK);
-                    }
-                    const int nb = live_blocks(t);                  // GEMM2 operand, first half of tile t
-                    for (int j = 0; j < 2 && j < nb; ++j) load_b2(b2_row0 + t * BN + j * BK);
+                    if (t + 1 < tiles) load_b1(row0 + (t + 1) * BN);
+                    const int nb = live_blocks(t);
+                    for (int j = 0; j < nb; ++j) load_b2(row0 + t * BN + j * BK);
                 }
-                const int nb = live_blocks(tiles - 1);
-                for (int j = 2; j < nb; ++j) load_b2(b2_row0 + (tiles - 1) * BN + j * BK);
+            }
+        }
+    } else if (warp == 3) {
+        // ================= A1 producer: the stationary operand, one k-block at a time =================
+        if (lane == 0) {
+            uint32_t n_item = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                int a_row;
+                if (DX) {
+                    const int b = item / p.PT;
+                    a_row = b * HW + (item - b * p.PT) * BM;        // this item's 128 pixels of X
+                } else {
+                    a_row = (item % p.MT) * BM;                     // this item's 128 channels of W
+                }
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    mbar_wait(a_empty + kb, (n_item & 1) ^ 1);
+                    mbar_expect_tx(a_full + kb, (uint32_t)A_KB_BYTES);
+                    tma_load_2d(sA + kb * A_KB_BYTES, &map_a, kb * BK, a_row, a_full + kb);
+                }
             }
         }
     } else if (warp == 1) {
@@ -207,6 +236,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(b_full + s, ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sS + j * STG_BLK_BYTES), b_addr = smem_u32(sB + s * STAGE_BYTES);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                    if (p.dbg & 8) { tc_commit(b_empty + s); continue; }
+#endif
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
                         // A: K-major, +32 B per 16 contraction columns; B: MN-major, 16 contraction rows = 2 groups of 8 = +2 KiB
@@ -216,42 +248,52 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     tc_commit(b_empty + s);
                 }
             };
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-                mbar_wait(a_full, n_item & 1);
+            // GEMM1 of one tile; first = the item's first tile (A1 k-blocks may still be landing), last = its last (hand A1 back per k-block)
+            auto gemm1 = [&](bool first, bool last, uint32_t item_parity) {
+                K4_STAMP(tile_it, 0);
+                mbar_wait(d1_empty, (tile_it & 1) ^ 1);         // the epilogue has pulled the previous tile out of D1
                 tc_fence_after();
-                acc2 = 0;
-                for (int t = 0; t < tiles; ++t, ++tile_it) {
-                    const uint32_t tp = tile_it & 1;
-                    mbar_wait(d1_empty, tp ^ 1);                // the epilogue holds the previous tile in registers
+                K4_STAMP(tile_it, 1);
+                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    if (first) mbar_wait(a_full + kb, item_parity);
+                    mbar_wait(b_full + s, ph);
                     tc_fence_after();
-                    for (int kb = 0; kb < p.KB; ++kb, ++it) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(b_full + s, ph);
-                        tc_fence_after();
-                        const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * STAGE_BYTES));
+                    const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * STAGE_BYTES));
 #pragma unroll
-                        for (int k16 = 0; k16 < BK / 16; ++k16) umma(tmem_d1, ad + 2 * k16, bd + 2 * k16, kIdesc1, (uint32_t)((kb | k16) != 0));
-                        tc_commit(b_empty + s);
-                    }
-                    tc_commit(d1_full);
-                    if (t > 0) {            // second half of the previous tile: its dH has been in the staging buffer for a while
-                        mbar_wait(s_full + 1, tp ^ 1);
-                        tc_fence_after();
-                        gemm2(2, live_blocks(t - 1));
-                        tc_commit(s_empty + 1);
-                    }
-                    if (t == 0) mbar_wait(d2_empty, (n_item & 1) ^ 1);     // the previous item's D2 has been drained (GEMM1 above overlapped the drain)
-                    mbar_wait(s_full + 0, tp);          // first half of this tile (the epilogue is working on it right now)
-                    tc_fence_after();
-                    gemm2(0, min(2, live_blocks(t)));
-                    tc_commit(s_empty + 0);
+                    for (int k16 = 0; k16 < BK / 16; ++k16) umma(tmem_d1, ad + 2 * k16, bd + 2 * k16, kIdesc1, (uint32_t)((kb | k16) != 0));
+                    tc_commit(b_empty + s);
+                    if (last) tc_commit(a_empty + kb);
                 }
-                mbar_wait(s_full + 1, (tile_it & 1) ^ 1);       // second half of the item's last tile
+                tc_commit(d1_full);
+                K4_STAMP(tile_it, 2);
+                ++tile_it;
+            };
+            // GEMM2 block q of the tile whose epilogue phase parity is tp, nb live blocks
+            auto gemm2_block = [&](int q, int nb, uint32_t tp) {
+                mbar_wait(s_full + q, tp);
                 tc_fence_after();
-                gemm2(2, live_blocks(tiles - 1));
-                tc_commit(s_empty + 1);
+                gemm2(q, min(q + 1, nb));
+                tc_commit(s_empty + q);
+            };
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+                acc2 = 0;
+                gemm1(true, tiles == 1, n_item & 1);
+                for (int t = 0; t < tiles; ++t) {
+                    const uint32_t tp = (tile_it - 1) & 1;                 // tile t is GEMM1 number tile_it - 1 of this CTA
+                    // GEMM1 of the NEXT tile first: D1 is free as soon as the epilogue has pulled tile t into registers (a few hundred
+                    // clocks), while the four staging blocks of tile t only fill up over the whole of its epilogue
+                    if (t + 1 < tiles) gemm1(false, t + 2 == tiles, n_item & 1);
+                    if (t == 0) {
+                        mbar_wait(d2_empty, (n_item & 1) ^ 1);         // the previous item's D2 has been drained
+                        tc_fence_after();
+                    }
+                    K4_STAMP(tile_it - (t + 1 < tiles ? 2 : 1), 3);
+                    const int nb = live_blocks(t);
+                    for (int q = 0; q < NBLK; ++q) gemm2_block(q, nb, tp);
+                    K4_STAMP(tile_it - (t + 1 < tiles ? 2 : 1), 4);
+                }
                 tc_commit(d2_full);                             // D2 complete: every MMA of the item has finished
-                tc_commit(a_empty);
             }
         }
     } else if (warp >= 4) {
@@ -289,28 +331,34 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             float dsum = 0.f;
             for (int t = 0; t < tiles; ++t, ++tile_it) {
                 const uint32_t tp = tile_it & 1;
+                if (e == 0 && lane == 0) K4_STAMP(tile_it, 8);
                 mbar_wait(d1_full, tp);
                 tc_fence_after();
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const int col0 = h * 128 + cg * 32;                     // first of this warp's 32 columns in this half
-                    float v[32];
-                    tmem_ld32(tmem_base + lane_off + (uint32_t)col0, v);
-                    if (h == 1) {                                           // D1 is in registers: GEMM1 of the next tile may overwrite it
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_empty);
-                    }
-                    uint32_t o[16];
+                if (e == 0 && lane == 0) K4_STAMP(tile_it, 9);
+                // four steps of 64 columns (= staging block q = one GEMM2 k-block); this warp's 16 columns of step q are
+                // q * 64 + cg * 16 ..  Three register buffers: steps 0, 1, 2 are fetched up front, step 3 reuses buffer 0 as soon
+                // as step 0 has been computed -- D1 is released to the next GEMM1 before step 1 starts.
+                const uint32_t tbase = tmem_base + lane_off + (uint32_t)(cg * 16);
+                uint32_t r0[16], r1[16], r2[16];
+                tmem_ld16_issue(tbase, r0);
+                tmem_ld16_wait(r0);
+                if (e == 0 && lane == 0) K4_STAMP(tile_it, 10);
+                tmem_ld16_issue(tbase + 64, r1);
+                tmem_ld16_issue(tbase + 128, r2);
+#pragma unroll
+                for (int q = 0; q < NBLK; ++q) {
+                    uint32_t(&cur)[16] = (q == 1) ? r1 : ((q == 2) ? r2 : r0);
+                    const int col0 = q * 64 + cg * 16;              // first of this warp's 16 columns in this step
+                    uint32_t o[8];
                     uint64_t b01, g22;          // (base, base + g) and (2 g, 2 g): the weight of column i is base + i * g
                     uint64_t kk = 0;            // K4w: the row's exponent offset for every column
                     const uint8_t* kp = nullptr;    // K4x: per-column exponent offsets of this run, 4 columns per 16-byte load
                     if (DX) {
                         const int c0 = t * BN + col0;                       // first channel of the run (one joint: D % 32 == 0)
                         const float4 jc = __ldg(p.jtab + (size_t)b * p.Jpad + (c0 >> dshift));
-                        const float q = fmaf(jc.x, xf, fmaf(jc.y, yf, jc.w));
+                        const float qq = fmaf(jc.x, xf, fmaf(jc.y, yf, jc.w));
                         const float z0 = (float)(c0 & (p.D - 1));
-                        b01 = pk2(fmaf(jc.z, z0, q), fmaf(jc.z, z0 + 1.f, q));
+                        b01 = pk2(fmaf(jc.z, z0, qq), fmaf(jc.z, z0 + 1.f, qq));
                         g22 = pk2(2.f * jc.z, 2.f * jc.z);
                         kp = reinterpret_cast<const uint8_t*>(p.k0tab + (size_t)b * p.Mpad + c0);
                     } else {
@@ -322,8 +370,14 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         kk = pk2(k0_row, k0_row);
                     }
                     uint64_t ds2 = pk2(0.f, 0.f);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                    if (p.dbg & 2) {
 #pragma unroll
-                    for (int i2 = 0; i2 < 8; ++i2) {
+                        for (int i = 0; i < 8; ++i) o[i] = cur[2 * i] ^ cur[2 * i + 1];
+                    } else
+#endif
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
                         uint64_t ka = kk, kb2 = kk;
                         if (DX) {
                             const uint4 u = ldg_u4(kp + i2 * 16);
@@ -334,7 +388,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         for (int half = 0; half < 2; ++half) {
                             const int i = 2 * i2 + half;
                             float t0, t1, d0, d1;
-                            up2(ffma2(pk2(v[2 * i], v[2 * i + 1]), l2e2, half ? kb2 : ka), t0, t1);
+                            up2(ffma2(pk2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), l2e2, half ? kb2 : ka), t0, t1);
                             const uint64_t dd = fmul2(pk2(ex2(t0), ex2(t1)), ffma2(pk2((float)i, (float)i), g22, b01));
                             if (!DX) ds2 = fadd2(ds2, dd);
                             up2(dd, d0, d1);
@@ -346,41 +400,54 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         up2(ds2, da, db);
                         dsum += da + db;
                     }
-                    // GEMM2 of the tile before has read this half of the staging buffer
-                    if (lane == 0) mbar_wait(s_empty + h, tp ^ 1);
+                    if (q == 0) {
+                        tmem_ld16_issue(tbase + 192, r0);       // step 3's columns into the buffer step 0 has just finished with
+                        if (e == 0 && lane == 0) K4_STAMP(tile_it, 11);
+                        // the whole of D1 is in registers now: release it, GEMM1 of the next tile runs underneath the rest of this epilogue
+                        tmem_ld16_wait3(r1, r2, r0);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d1_empty);
+                        if (e == 0 && lane == 0) K4_STAMP(tile_it, 13);
+                    }
+                    // GEMM2 of the tile before has read this staging block
+                    if (lane == 0) mbar_wait(s_empty + q, tp ^ 1);
                     __syncwarp();
-                    // 32 columns = 64 B of this row: chunks (cg & 1) * 4 + i of the 128-byte row of staging block 2 h + (cg >> 1)
-                    uint8_t* srow = sS + (2 * h + (cg >> 1)) * STG_BLK_BYTES + row * 128;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        sts16(srow + (((((cg & 1) << 2) + i) ^ sw) << 4), make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                    // 16 columns = 32 B of this row: chunks 2 cg, 2 cg + 1 of the 128-byte row of staging block q
+                    uint8_t* srow = sS + q * STG_BLK_BYTES + row * 128;
+                    sts16(srow + (((2 * cg) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                    sts16(srow + (((2 * cg + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
                     fence_async_smem();             // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_full + h);
+                    if (lane == 0) mbar_arrive(s_full + q);
+                    if (q == 0 && e == 0 && lane == 0) K4_STAMP(tile_it, 12);
+                    if (q == 3 && e == 0 && lane == 0) K4_STAMP(tile_it, 14);
+
                 }
             }
             // ---- the item's second accumulator
             mbar_wait(d2_full, n_item & 1);
             tc_fence_after();
             if (DX) {
-                // dX tile [128 px x K] -> bf16 -> staging (every GEMM2 has completed: the buffer is free) -> TMA store, NHWC
+                // dX tile [128 px x K] -> bf16 in registers (D2 is free again at once) -> staging -> TMA store, NHWC.  Every GEMM2 of the
+                // item has completed, so the staging blocks are free.
+                uint32_t o[32];
                 if (cg < p.KB) {
-                    uint8_t* srow = sS + cg * STG_BLK_BYTES + row * 128;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         float v[32];
                         tmem_ld32(tmem_base + lane_off + D2_COL + (uint32_t)(cg * 64 + q * 32), v);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            sts16(srow + ((((q << 2) + i) ^ sw) << 4),
-                                  make_uint4(Elem<__nv_bfloat16>::pk(v[8 * i], v[8 * i + 1]), Elem<__nv_bfloat16>::pk(v[8 * i + 2], v[8 * i + 3]),
-                                             Elem<__nv_bfloat16>::pk(v[8 * i + 4], v[8 * i + 5]), Elem<__nv_bfloat16>::pk(v[8 * i + 6], v[8 * i + 7])));
+                        for (int i = 0; i < 16; ++i) o[q * 16 + i] = Elem<__nv_bfloat16>::pk(v[2 * i], v[2 * i + 1]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d2_empty);
                 if (cg < p.KB) {
+                    uint8_t* srow = sS + cg * STG_BLK_BYTES + row * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sts16(srow + ((i ^ sw) << 4), make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -509,6 +576,17 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
     off = (off + (size_t)B * 4 * p.Mpad * sizeof(float) + 255) / 256 * 256;
     float* dw_part = reinterpret_cast<float*>(ws + off);
     p.k0tab = k0tab; p.jtab = jtab; p.dw_part = dw_part; p.db_part = db_part;
+    p.dbg = 0;
+    p.trace = nullptr;
+#ifdef IHPR_TIMING_EXPERIMENTS
+    if (const char* e = getenv("IHPR_K4_DEBUG")) p.dbg = atoi(e);
+    static long long* d_trace = nullptr;
+    if (getenv("IHPR_K4_TRACE")) {
+        if (!d_trace) cudaMalloc(&d_trace, 64 * 16 * sizeof(long long));
+        cudaMemsetAsync(d_trace, 0, 64 * 16 * sizeof(long long), s);
+        p.trace = d_trace;
+    }
+#endif
 
     const float loss_scale = 1.0f / (3.0f * (float)B * (float)J);
     {
@@ -535,6 +613,26 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
         if (grid > num_sms) grid = num_sms;
         kern<<<grid, 32 * (4 + EPI_WARPS), smem, s>>>(map_w128, map_x256, map_x64, map_dx, p);
         ++*launches;
+#ifdef IHPR_TIMING_EXPERIMENTS
+        if (p.trace && getenv("IHPR_K4_TRACE")[0] == '2') {        // dump once: stamps relative to the first, per tile
+            static bool dumped = false;
+            if (!dumped) {
+                dumped = true;
+                long long h[64 * 16];
+                cudaStreamSynchronize(s);
+                cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+                const long long t0 = h[0];
+                fprintf(stderr, "K4w trace of CTA 0 (clk since first stamp): tile | issuer: wait_d1e got_d1e g1_issued wait_s0 got_s0 | epilogue: wait_d1f got_d1f ld0 step0_math staged0 d1_released step3_staged\n");
+                for (int t = 0; t < 34; ++t) {
+                    fprintf(stderr, "%2d |", t);
+                    for (int k = 0; k < 5; ++k) fprintf(stderr, " %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+                    fprintf(stderr, " |");
+                    for (int k = 8; k < 15; ++k) fprintf(stderr, " %7lld", h[t * 16 + k] ? h[t * 16 + k] - t0 : -1);
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+#endif
         const int n = p.M * K, th = 256;
         head_bwd_reduce_kernel<<<(n + th - 1) / th, th, 0, s>>>(dw_part, db_part, B, p.M, p.Mpad, K, p.MT, dweight, dbias);
         ++*launches;

@@ -210,12 +210,6 @@ head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __g
                         const uint64_t l2e2 = pk2(kLog2e, kLog2e), k02 = pk2(k0, k0);
                         const uint64_t b01 = pk2(base, base + gx), gx22 = pk2(2.f * gx, 2.f * gx);
                         uint64_t ds2 = pk2(0.f, 0.f);
-#ifdef IHPR_TIMING_EXPERIMENTS
-                        if (p.dbg & 2) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(v[2 * i]) ^ __float_as_uint(v[2 * i + 1]);
-                        } else
-#endif
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float t0, t1, d0, d1;
@@ -242,21 +236,7 @@ head_softargmax_pair_kernel(const __grid_constant__ CUtensorMap map_w, const __g
                     // at B = 32; staging + 64-byte STG segments: 103 us)
                     fence_async_smem();
                     __syncwarp();
-#ifdef IHPR_TIMING_EXPERIMENTS
-                    if (p.dbg & 1) continue;
-#endif
                     if (lane == 0) {
-#ifdef IHPR_TIMING_EXPERIMENTS
-                        if (p.dbg & 16) {       // blocked layout: this warp's 4 KiB tile to one contiguous block (WRONG layout, timing only)
-                            uint8_t* dst = reinterpret_cast<uint8_t*>(p.grad_heat) + ((((size_t)item * p.NT + nt) * EPI_WARPS + e) << 12);
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(dst), "r"(smem_u32(wstg)) : "memory");
-                        } else if (p.dbg & 12) {
-                            uint64_t pol;
-                            if (p.dbg & 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-                            else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-                            tma_store_3d_hint(&map_g, wstg, nt * BN + ch * CW, mt * BM + qd * 32, b, pol);
-                        } else
-#endif
                         tma_store_3d(&map_g, wstg, nt * BN + ch * CW, mt * BM + qd * 32, b);
                         tma_store_commit();
                     }

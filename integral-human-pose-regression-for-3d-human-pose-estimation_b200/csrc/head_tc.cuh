@@ -134,6 +134,12 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
+// wait for every outstanding tcgen05.ld of this warp; the three arrays named are the ones whose loads were in flight
+__device__ __forceinline__ void tmem_ld16_wait3(uint32_t (&a)[16], uint32_t (&b)[16], uint32_t (&c)[16]) {
+    tmem_ld16_wait(a);
+    tmem_ld16_wait(b);
+    tmem_ld16_wait(c);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
