@@ -515,16 +515,17 @@ def train_core(args, dev, world, rank, resnet, fused_head, crit_kind, cuda_graph
     elif crit_kind == "unfused":
         crit = ihpr_b200.JointLocationLoss(fused_backward=False)
     tr = Trainer(net, cfg, criterion=crit, device=dev, autocast_dtype=torch.bfloat16 if args.precision == "bf16" else None,
-                 channels_last=True, static_graph=False)
+                 channels_last=True, static_graph=False, graph_capture=cuda_graph)
     host = synthetic_batch(B, J, cfg, None, seed=100 + rank, pin=True)
     devb = [t.to(dev) for t in host]
-    for _ in range(max(warmup, 5)):
-        tr.train_step(*devb)
+    if not cuda_graph:          # (with --cuda-graph the warm-up steps run inside capture(), on the stream the graph is captured on)
+        for _ in range(max(warmup, 5)):
+            tr.train_step(*devb)
     torch.cuda.synchronize()
     K = steps
     step_fn = tr.train_step
     if cuda_graph:
-        tr.capture(*devb)
+        tr.capture(*devb, warmup=max(warmup, 5))
         step_fn = tr.graphed_step
         for _ in range(3):
             step_fn(*devb)

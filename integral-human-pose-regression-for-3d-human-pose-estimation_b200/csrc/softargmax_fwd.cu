@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) fwd_ring_kernel(const Fwd
     const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NC / Fv), hf = u2f((uint32_t)g.H);
     Acc a;
     a.reset();
+    uint64_t w2 = 0;            // fast path: packed within-vector x moment (ihpr_device.cuh: consume_chunk_fast_pk)
     uint32_t it = 0, rowseq = 0;
     for (uint64_t gi = g_lo; gi < g_hi; ++gi, ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -85,22 +86,22 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) fwd_ring_kernel(const Fwd
         const uint8_t* st = ring + (size_t)s * CHUNK_BYTES;
         auto load = [&](uint32_t iv) { return lds16(st + (size_t)iv * 16); };
         if (fast) {
-            if (n_vec == VPC) consume_chunk_fast<T, U, NC, VPC, true>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
-            else consume_chunk_fast<T, U, NC, VPC, false>(a, g, n_vec, k * VPC, tid, rsf, hf, load);
+            if (n_vec == VPC) consume_chunk_fast_pk<T, U, NC, VPC, true>(a, w2, g, n_vec, k * VPC, tid, rsf, hf, load);
+            else consume_chunk_fast_pk<T, U, NC, VPC, false>(a, w2, g, n_vec, k * VPC, tid, rsf, hf, load);
         } else {
             consume_chunk<T, U, NC>(a, g, n_vec, e0 >> 2, tid, load);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
         if (++k == g.nch) {
-            if (fast) a.sx = fmaf(x0f, a.l, a.sx);
+            if (fast) { fold_w2(a, w2); a.sx = fmaf(x0f, a.l, a.sx); }
             flush_row_async<NCW, NBUF>(p, (int)r, a, pbuf, pcnt, rowseq++, wid, lane, cta, G);
             a.reset();
             k = 0; ++r;
         }
     }
     if (k != 0) {
-        if (fast) a.sx = fmaf(x0f, a.l, a.sx);
+        if (fast) { fold_w2(a, w2); a.sx = fmaf(x0f, a.l, a.sx); }
         flush_row_async<NCW, NBUF>(p, (int)r, a, pbuf, pcnt, rowseq++, wid, lane, cta, G);
     }
 }

@@ -99,7 +99,10 @@ def predict_sharded(model, input_img_local, flip_pairs=None, group=None):
 
 
 class Trainer:
-    def __init__(self, model, cfg=DEFAULT_CFG, criterion=None, device=None, autocast_dtype=None, channels_last=False, static_graph=True):
+    def __init__(self, model, cfg=DEFAULT_CFG, criterion=None, device=None, autocast_dtype=None, channels_last=False, static_graph=True,
+                 graph_capture=False):
+        """graph_capture=True (multi-GPU only matters): build DDP on the side stream that capture() will later capture on -- PyTorch's
+        recipe for CUDA graphs under DDP (its gradient-accumulation nodes remember the stream they were created on)."""
         self.cfg = cfg
         self.device = device if device is not None else torch.device("cpu")
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -111,11 +114,18 @@ class Trainer:
         if criterion is not None:
             model.criterion = criterion
         self.raw_model = model
+        self._side = torch.cuda.Stream(self.device) if (graph_capture and self.device.type == "cuda") else None
         if self.world > 1:
             ids = [self.device.index] if self.device.type == "cuda" else None
             # BN running statistics stay per rank, as in the reference's replicas (no SyncBN, balanced_parallel.py:16-43 is dead code)
-            self.model = DDP(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=25, broadcast_buffers=False,
-                             static_graph=static_graph)
+            ctx = torch.cuda.stream(self._side) if self._side is not None else _null()
+            if self._side is not None:
+                self._side.wait_stream(torch.cuda.current_stream(self.device))
+            with ctx:
+                self.model = DDP(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=25, broadcast_buffers=False,
+                                 static_graph=static_graph)
+            if self._side is not None:
+                torch.cuda.current_stream(self.device).wait_stream(self._side)
         else:
             self.model = model
         # base.py:75-77 (Adam, lr from the config); the fused multi-tensor implementation when the parameters are on a GPU.
@@ -209,7 +219,7 @@ class Trainer:
         self._static = [t.clone() for t in (input_img, joint_img, joint_vis, joints_have_depth)]
         if self.channels_last:
             self._static[0] = self._static[0].contiguous(memory_format=torch.channels_last)
-        side = torch.cuda.Stream(self.device)
+        side = self._side if self._side is not None else torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -219,7 +229,7 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         self._graph = torch.cuda.CUDAGraph()
 
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):
             loss = self._forward_backward(self.model, *self._static)
             self.optimizer.step()
         self._static_loss = loss.detach()

@@ -777,5 +777,7 @@ def test_two_rank_nccl_step_equals_single_process(fused, dev, tmp_path):
     assert abs(got["loss"].item() - loss.item()) <= tol * max(1.0, abs(loss.item()))
     for key, par in (("gw", net.head.final_layer.weight), ("gc", net.backbone.conv1.weight)):
         ref = par.grad.float().cpu()                           # DDP leaves the rank-averaged gradient in .grad
-        assert (got[key] - ref).abs().max().item() <= (3e-2 if fused else 2e-3) * ref.abs().max().item(), key
+        # conv1's gradient is ~1e-14 here (std-1e-3 init through 50 layers): cuDNN's summation order alone moves it by a percent
+        tol = 3e-2 if (fused or key == "gc") else 2e-3
+        assert (got[key] - ref).abs().max().item() <= tol * ref.abs().max().item(), key
     assert (got["coords"] - coords.cpu()).abs().max().item() <= (0.05 if fused else 1e-3)
