@@ -216,8 +216,9 @@ int ihpr_host_release(int device);
 /* Tuning / introspection (does not change results beyond rounding; the setting belongs to the CALLING THREAD): kernel variant 0 = auto,
  * 1 = TMA-bulk shared-memory ring, 2 = direct 128-bit global loads; for ihpr_integral_l1_fwd_bwd
  * 7 = cluster-resident K5c where it applies, 8 = the one-launch form whenever it applies (no measurement), 9 = always the
- * two-kernel sequence; for the fused-head entries
- * 5 = the SM-pair (tcgen05 cta_group::2) form of K3 / K4 (bit-identical results, slower on B200: profiles/r01_ncu_K4.txt). */
+ * two-kernel sequence; for ihpr_head_integral_l1_bwd_params 3 = both kernels on SM pairs (tcgen05.mma.cta_group::2; bit-identical results,
+ * slower on B200: profiles/r02_head_bench_pairs.txt); for the Python autograd wrapper 6 = the comparison arm (K4 heat-map gradient +
+ * library GEMMs). */
 int ihpr_set_variant(int variant);
 int ihpr_get_variant(void);
 /* Number of kernels the LAST call on this thread launched (for bench.py's gpu_launches). */

@@ -496,12 +496,8 @@ static int head_common(const void* x_nhwc, const void* weight, const float* bias
     int num_sms = 0;
     int rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
-    // variant 5: the SM-pair (cta_group::2) form of K3 / K4
-    const bool pairs = g_variant == 5 && num_sms >= 2;
-    const char* err = pairs ? ihpr::launch_head_fused_pair(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat,
-                                                           dbias_part, num_sms, static_cast<cudaStream_t>(stream))
-                            : ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part,
-                                                      num_sms, static_cast<cudaStream_t>(stream));
+    const char* err = ihpr::launch_head_fused(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, hd, grad_out, grad_heat, dbias_part,
+                                              num_sms, static_cast<cudaStream_t>(stream));
     if (err) return fail(IHPR_ECUDA, "%s", err);
     g_launches = 1;
     IHPR_CUDA(cudaGetLastError());
@@ -539,8 +535,11 @@ int ihpr_head_integral_l1_bwd_params(const void* x_nhwc, const void* weight, con
     rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
     int launches = 0;
+    // variant 3: both kernels on SM pairs (tcgen05.mma.cta_group::2: half the operand traffic per SM) -- bit-identical results, measured
+    // 1.6x slower than one CTA per SM on B200 (profiles/r02_head_bench_pairs.txt), so it is opt-in
+    const int pairs = g_variant == 3 ? 3 : 0;
     const char* err = ihpr::launch_head_bwd_params(x_nhwc, weight, bias, B, K, J, D, H, W, coords, stats, gt, vis, have_depth, grad_out, dx_nhwc, dweight,
-                                                   dbias, workspace, num_sms, &launches, static_cast<cudaStream_t>(stream));
+                                                   dbias, workspace, num_sms, pairs, &launches, static_cast<cudaStream_t>(stream));
     if (err) return fail(IHPR_ECUDA, "%s", err);
     g_launches = launches;
     IHPR_CUDA(cudaGetLastError());

@@ -47,6 +47,7 @@ constexpr int BN = 256;                 // columns of the heat-map tile
 constexpr int BK = 64;                  // one SWIZZLE_128B row of bf16
 constexpr int MAXKB = 4;                // C_in <= 256
 constexpr int STAGES = 3;               // operand ring: 32 KiB stages shared by B1 k-blocks and B2 blocks, strictly FIFO in the issuer's order
+constexpr int STAGES_PAIR = 6;          // SM-pair form: each CTA holds HALF of every stage (16 KiB), so the same 96 KiB are six stages deep
 constexpr int NSTG = 4;                 // staging blocks: the whole bf16 gradient tile (64 KiB) -- GEMM2 of tile t runs AFTER GEMM1 of tile t+1
 constexpr int A_KB_BYTES = BM * BK * 2;         // 16 KiB
 constexpr int STAGE_BYTES = BN * BK * 2;        // 32 KiB
@@ -94,6 +95,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, u
 // instruction descriptor with a runtime N and an MN-major B operand (bit 16)
 __device__ __forceinline__ uint32_t idesc_bmn(int N) { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 constexpr uint32_t kIdesc1 = make_idesc(BM, BN);
+constexpr uint32_t kIdesc1Pair = make_idesc(2 * BM, BN);        // cta_group::2: M = 256 over the two CTAs
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src))
@@ -115,19 +117,27 @@ __device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
 //   map_b1: GEMM1's streamed operand, box 64 x 256  (K4w: X,  K4x: W)
 //   map_b2: GEMM2's streamed operand, box 64 x 64   (K4w: X,  K4x: W)  -- the same tensor as B1, other box
 //   map_dx: K4x only: d loss / d x, (B*H*W, K) bf16, box 64 x 32 rows (one epilogue warp's slice)
-template <bool DX>
+// PAIR = true: the two CTAs of a cluster run every UMMA together (tcgen05.mma.cta_group::2, M = 256): each CTA owns its own 128 rows
+// (its A1, its D1 / D2 in its own TMEM, its own epilogue and staging buffer) and loads only HALF of every streamed operand stage --
+// GEMM1's B1 is split by its 256 N rows, GEMM2's MN-major B2 by its C_in columns (n-blocks) -- so the L2 -> SM traffic per SM, which is
+// what bounds the single-CTA form (256 KiB per tile against ~42 B/clk of ingress: ~6200 clk per tile for 4096 clk of MMA work), halves.
+// Rank 0 issues all MMAs; its barriers collect both CTAs' TMA bytes and epilogue arrivals; tcgen05.commit multicasts to both.
+template <bool DX, bool PAIR>
 __global__ void __launch_bounds__(32 * (4 + EPI_WARPS), 1)
 head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
                 const __grid_constant__ CUtensorMap map_dx, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                     // [KB][128 x 64] bf16, stationary per item
-    uint8_t* sB = sA + MAXKB * A_KB_BYTES;                  // [STAGES][32 KiB]
-    uint8_t* sS = sB + STAGES * STAGE_BYTES;                // [4][128 x 64] bf16: dH of one tile = GEMM2's A operand, one k-block per staging block
+    constexpr int NST = PAIR ? STAGES_PAIR : STAGES;        // ring depth
+    constexpr int STB = PAIR ? STAGE_BYTES / 2 : STAGE_BYTES;   // bytes of a stage in THIS CTA
+    constexpr uint32_t NCTA = PAIR ? 2 : 1;
+    uint8_t* sB = sA + MAXKB * A_KB_BYTES;                  // [NST][STB]
+    uint8_t* sS = sB + NST * STB;                // [4][128 x 64] bf16: dH of one tile = GEMM2's A operand, one k-block per staging block
     uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSTG * STG_BLK_BYTES);
-    uint64_t* b_full = bars;                    // [STAGES] TMA -> MMA
-    uint64_t* b_empty = b_full + STAGES;        // [STAGES] MMA -> TMA
-    uint64_t* a_full = b_empty + STAGES;        // [MAXKB] A1 k-block landed
+    uint64_t* b_full = bars;                    // [NST] TMA -> MMA
+    uint64_t* b_empty = b_full + NST;           // [NST] MMA -> TMA
+    uint64_t* a_full = b_empty + NST;           // [MAXKB] A1 k-block landed
     uint64_t* a_empty = a_full + MAXKB;         // [MAXKB] the item's last GEMM1 has read A1 k-block kb
     uint64_t* d1_full = a_empty + MAXKB;        // [1]  MMA -> epilogue: heat-map tile complete
     uint64_t* d1_empty = d1_full + 1;           // [1]  epilogue -> MMA: D1 is in registers (EPI_WARPS arrivals)
@@ -138,25 +148,50 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = DX ? p.B * p.PT : p.B * p.MT;
+    const uint32_t rank = PAIR ? pair_rank() : 0;           // 0 = leader (issues the MMAs)
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // a work item of a pair = two adjacent 128-row items of the same sample (K4w: channel tiles 2 i, 2 i + 1; K4x: pixel tiles); an odd
+    // number of channel tiles leaves a dead CTA in the last pair of every sample (its W rows are zero-filled, its tables say weight 0)
+    const int per_sample = DX ? p.PT : p.MT;
+    const int ips = PAIR ? (per_sample + 1) / 2 : per_sample;           // items per sample
+    const int items = p.B * ips;
     const int tiles = DX ? p.CB : p.NT;                 // GEMM1 tiles per item
     const int HW = p.H * p.W;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int kb = 0; kb < MAXKB; ++kb) { mbar_init(a_full + kb, 1); mbar_init(a_empty + kb, 1); }
-        mbar_init(d1_full, 1); mbar_init(d1_empty, EPI_WARPS);
-        for (int u = 0; u < NSTG; ++u) { mbar_init(s_full + u, EPI_WARPS); mbar_init(s_empty + u, 1); }
-        mbar_init(d2_full, 1); mbar_init(d2_empty, EPI_WARPS);
+        mbar_init(d1_full, 1); mbar_init(d1_empty, NCTA * EPI_WARPS);
+        for (int u = 0; u < NSTG; ++u) { mbar_init(s_full + u, NCTA * EPI_WARPS); mbar_init(s_empty + u, 1); }
+        mbar_init(d2_full, 1); mbar_init(d2_empty, NCTA * EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) pair_sync();      // the peer's barriers exist and its TMEM is allocated before anything is signalled across the pair
     tc_fence_after();
+    // item -> sample and this CTA's 128-row index within the sample (K4w: channel tile, may be the dead one; K4x: pixel tile)
+    auto item_b = [&](int item) { return item / ips; };
+    auto item_row = [&](int item) { const int i = item - (item / ips) * ips; return PAIR ? 2 * i + (int)rank : i; };
+    // barrier of the leader CTA as seen from this one (this CTA's own when there is no pair)
+    auto lead = [&](uint64_t* bar) -> uint32_t { return PAIR ? pair_addr(bar, 0) : smem_u32(bar); };
+    auto arrive_lead = [&](uint64_t* bar) {        // epilogue -> issuer
+        if (PAIR) mbar_arrive_cluster(pair_addr(bar, 0));
+        else mbar_arrive(bar);
+    };
+    auto load_2d = [&](void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {      // bytes are counted on the leader's barrier
+        if (PAIR) tma_load_2d_pair(dst, map, c0, c1, pair_addr(bar, 0));
+        else tma_load_2d(dst, map, c0, c1, bar);
+    };
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     // live 64-column blocks of tile t (K4x: the last channel block of J*D may be partial; its missing W rows are zero-filled by TMA)
@@ -170,30 +205,31 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t it = 0, n_item = 0;
-            auto load_b2 = [&](int row0) {       // one GEMM2 block: KB boxes of [64 contraction rows x 64 n], n-block kb at +kb * 8 KiB
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            const int nsub = PAIR ? p.KB / 2 : p.KB;        // n-blocks of a GEMM2 operand block this CTA loads (the pair splits C_in)
+            auto load_b2 = [&](int row0) {       // one GEMM2 block: boxes of [64 contraction rows x 64 n], n-block i at +i * 8 KiB
+                const uint32_t s = it % NST, ph = (it / NST) & 1;
                 mbar_wait(b_empty + s, ph ^ 1);
 #ifdef IHPR_TIMING_EXPERIMENTS
-                if (p.dbg & 1) { mbar_arrive(b_full + s); ++it; return; }
+                if (!PAIR && (p.dbg & 1)) { mbar_arrive(b_full + s); ++it; return; }
 #endif
-                mbar_expect_tx(b_full + s, (uint32_t)(p.KB * B2_SUB_BYTES));
-                for (int kb = 0; kb < p.KB; ++kb) tma_load_2d(sB + s * STAGE_BYTES + kb * B2_SUB_BYTES, &map_b2, kb * BK, row0, b_full + s);
+                if (rank == 0) mbar_expect_tx(b_full + s, (uint32_t)(p.KB * B2_SUB_BYTES));
+                for (int i = 0; i < nsub; ++i) load_2d(sB + s * STB + i * B2_SUB_BYTES, &map_b2, ((int)rank * nsub + i) * BK, row0, b_full + s);
                 ++it;
             };
             auto load_b1 = [&](int row0) {       // GEMM1 operand of one tile: KB stages of [256 rows x 64 k]
                 for (int kb = 0; kb < p.KB; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1;
                     mbar_wait(b_empty + s, ph ^ 1);
 #ifdef IHPR_TIMING_EXPERIMENTS
-                    if (p.dbg & 4) { mbar_arrive(b_full + s); continue; }
+                    if (!PAIR && (p.dbg & 4)) { mbar_arrive(b_full + s); continue; }
 #endif
-                    mbar_expect_tx(b_full + s, (uint32_t)STAGE_BYTES);
-                    tma_load_2d(sB + s * STAGE_BYTES, &map_b1, kb * BK, row0, b_full + s);
+                    if (rank == 0) mbar_expect_tx(b_full + s, (uint32_t)STAGE_BYTES);
+                    load_2d(sB + s * STB, &map_b1, kb * BK, row0 + (PAIR ? (int)rank * (BN / 2) : 0), b_full + s);     // the pair splits the 256 N rows
                 }
             };
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+            for (int item = unit; item < items; item += nunits, ++n_item) {
                 // K4x: W rows of channel block t are t * 256; K4w: X rows of pixel tile t are b * HW + t * 256
-                const int row0 = DX ? 0 : (item / p.MT) * HW;
+                const int row0 = DX ? 0 : item_b(item) * HW;
                 // the issuer's order: GEMM1(0); per tile t: GEMM1(t+1), then GEMM2 blocks 0..3 of t
                 load_b1(row0);
                 for (int t = 0; t < tiles; ++t) {
@@ -207,45 +243,49 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================= A1 producer: the stationary operand, one k-block at a time =================
         if (lane == 0) {
             uint32_t n_item = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-                int a_row;
-                if (DX) {
-                    const int b = item / p.PT;
-                    a_row = b * HW + (item - b * p.PT) * BM;        // this item's 128 pixels of X
-                } else {
-                    a_row = (item % p.MT) * BM;                     // this item's 128 channels of W
-                }
+            for (int item = unit; item < items; item += nunits, ++n_item) {
+                // K4x: this CTA's 128 pixels of X; K4w: its 128 channels of W (all out of bounds -> zero-filled for the dead CTA of a pair)
+                const int a_row = DX ? item_b(item) * HW + item_row(item) * BM : item_row(item) * BM;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(a_empty + kb, (n_item & 1) ^ 1);
-                    mbar_expect_tx(a_full + kb, (uint32_t)A_KB_BYTES);
-                    tma_load_2d(sA + kb * A_KB_BYTES, &map_a, kb * BK, a_row, a_full + kb);
+                    if (rank == 0) mbar_expect_tx(a_full + kb, NCTA * (uint32_t)A_KB_BYTES);
+                    load_2d(sA + kb * A_KB_BYTES, &map_a, kb * BK, a_row, a_full + kb);
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, n_item = 0, tile_it = 0;
-            const uint32_t idesc2 = idesc_bmn(p.K);
+            const uint32_t idesc1 = PAIR ? kIdesc1Pair : kIdesc1;
+            const uint32_t idesc2 = idesc_bmn(p.K) + (PAIR ? ((uint32_t)(BM >> 4) << 24) : 0u);        // M = 256 for the pair
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+                if (PAIR) umma_pair(d, a, b, idesc, acc);
+                else umma(d, a, b, idesc, acc);
+            };
+            auto commit = [&](uint64_t* bar) {      // arrives on `bar` (in both CTAs of a pair) when every MMA issued so far has completed
+                if (PAIR) tc_commit_pair(bar);
+                else tc_commit(bar);
+            };
             const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + D2_COL;
             uint32_t acc2 = 0;
             // GEMM2 on staging blocks [j0, j1) of a tile: D2 += dH[:, 64 j .. 64 j + 63] . B2 block
             auto gemm2 = [&](int j0, int j1) {
                 for (int j = j0; j < j1; ++j, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1;
                     mbar_wait(b_full + s, ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sS + j * STG_BLK_BYTES), b_addr = smem_u32(sB + s * STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(sS + j * STG_BLK_BYTES), b_addr = smem_u32(sB + s * STB);
 #ifdef IHPR_TIMING_EXPERIMENTS
-                    if (p.dbg & 8) { tc_commit(b_empty + s); continue; }
+                    if (!PAIR && (p.dbg & 8)) { tc_commit(b_empty + s); continue; }
 #endif
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
                         // A: K-major, +32 B per 16 contraction columns; B: MN-major, 16 contraction rows = 2 groups of 8 = +2 KiB
-                        umma(tmem_d2, umma_desc(a_addr) + 2 * k16, umma_desc_mn(b_addr + k16 * 2048, B2_SUB_BYTES, 1024), idesc2, acc2);
+                        mma(tmem_d2, umma_desc(a_addr) + 2 * k16, umma_desc_mn(b_addr + k16 * 2048, B2_SUB_BYTES, 1024), idesc2, acc2);
                         acc2 = 1;
                     }
-                    tc_commit(b_empty + s);
+                    commit(b_empty + s);
                 }
             };
             // GEMM1 of one tile; first = the item's first tile (A1 k-blocks may still be landing), last = its last (hand A1 back per k-block)
@@ -255,17 +295,17 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_fence_after();
                 K4_STAMP(tile_it, 1);
                 for (int kb = 0; kb < p.KB; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1;
                     if (first) mbar_wait(a_full + kb, item_parity);
                     mbar_wait(b_full + s, ph);
                     tc_fence_after();
-                    const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * STAGE_BYTES));
+                    const uint64_t ad = umma_desc(smem_u32(sA + kb * A_KB_BYTES)), bd = umma_desc(smem_u32(sB + s * STB));
 #pragma unroll
-                    for (int k16 = 0; k16 < BK / 16; ++k16) umma(tmem_d1, ad + 2 * k16, bd + 2 * k16, kIdesc1, (uint32_t)((kb | k16) != 0));
-                    tc_commit(b_empty + s);
-                    if (last) tc_commit(a_empty + kb);
+                    for (int k16 = 0; k16 < BK / 16; ++k16) mma(tmem_d1, ad + 2 * k16, bd + 2 * k16, idesc1, (uint32_t)((kb | k16) != 0));
+                    commit(b_empty + s);
+                    if (last) commit(a_empty + kb);
                 }
-                tc_commit(d1_full);
+                commit(d1_full);
                 K4_STAMP(tile_it, 2);
                 ++tile_it;
             };
@@ -274,9 +314,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(s_full + q, tp);
                 tc_fence_after();
                 gemm2(q, min(q + 1, nb));
-                tc_commit(s_empty + q);
+                commit(s_empty + q);
             };
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
+            for (int item = unit; item < items; item += nunits, ++n_item) {
                 acc2 = 0;
                 gemm1(true, tiles == 1, n_item & 1);
                 for (int t = 0; t < tiles; ++t) {
@@ -293,7 +333,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int q = 0; q < NBLK; ++q) gemm2_block(q, nb, tp);
                     K4_STAMP(tile_it - (t + 1 < tiles ? 2 : 1), 4);
                 }
-                tc_commit(d2_full);                             // D2 complete: every MMA of the item has finished
+                commit(d2_full);                                // D2 complete: every MMA of the item has finished
             }
         }
     } else if (warp >= 4) {
@@ -308,21 +348,19 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int dshift = 31 - __clz(p.D);         // D is a power of two (32 / 64 / 128)
         const uint64_t l2e2 = pk2(kLog2e, kLog2e);
         uint32_t tile_it = 0, n_item = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_item) {
-            int b;
+        for (int item = unit; item < items; item += nunits, ++n_item) {
+            const int b = item_b(item), irow = item_row(item);
             // per-row constants
             float k0_row = 0.f, gx_row = 0.f, gy_row = 0.f, tz_row = 0.f;       // K4w: this channel
             float xf = 0.f, yf = 0.f;                                           // K4x: this pixel
             int c_row = 0;
             if (DX) {
-                b = item / p.PT;
-                const uint32_t pix = (uint32_t)((item - b * p.PT) * BM + row);
+                const uint32_t pix = (uint32_t)(irow * BM + row);
                 const uint32_t y = fdiv(pix, divW);
                 yf = u2f(y);
                 xf = u2f(pix - y * divW.d);
             } else {
-                b = item / p.MT;
-                c_row = (item - b * p.MT) * BM + row;               // < Mpad: the tables are padded
+                c_row = irow * BM + row;                            // < Mpad: the tables are padded (dead CTA of a pair included)
                 k0_row = __ldg(p.k0tab + (size_t)b * p.Mpad + c_row);
                 const float4 jc = __ldg(p.jtab + (size_t)b * p.Jpad + (c_row >> dshift));
                 gx_row = jc.x; gy_row = jc.y;
@@ -407,7 +445,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         tmem_ld16_wait3(r1, r2, r0);
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_empty);
+                        if (lane == 0) arrive_lead(d1_empty);
                         if (e == 0 && lane == 0) K4_STAMP(tile_it, 13);
                     }
                     // GEMM2 of the tile before has read this staging block
@@ -419,7 +457,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     sts16(srow + (((2 * cg + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
                     fence_async_smem();             // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_full + q);
+                    if (lane == 0) arrive_lead(s_full + q);
                     if (q == 0 && e == 0 && lane == 0) K4_STAMP(tile_it, 12);
                     if (q == 3 && e == 0 && lane == 0) K4_STAMP(tile_it, 14);
 
@@ -443,7 +481,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d2_empty);
+                if (lane == 0) arrive_lead(d2_empty);
                 if (cg < p.KB) {
                     uint8_t* srow = sS + cg * STG_BLK_BYTES + row * 128;
 #pragma unroll
@@ -451,7 +489,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        const int px_row = b * HW + (item - b * p.PT) * BM + qd * 32;
+                        const int px_row = b * HW + irow * BM + qd * 32;
                         tma_store_2d(&map_dx, sS + cg * STG_BLK_BYTES + qd * 32 * 128, cg * BK, px_row);
                         tma_store_commit();
                         tma_store_wait_read();      // the staging rows may be rewritten once the store has read them
@@ -461,9 +499,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 named_bar_sync(1, EPI_WARPS * 32);
             } else {
                 // dW partial [128 channels x K] fp32 -> workspace, 256 contiguous bytes per thread and 64-column group
-                const bool warp_live = (item - b * p.MT) * BM + qd * 32 < p.M;     // 32 consecutive channels: live or dead together (M % 32 == 0)
+                const bool warp_live = irow * BM + qd * 32 < p.M;     // 32 consecutive channels: live or dead together (M % 32 == 0)
                 if (cg < p.KB && warp_live) {
-                    float* dst = p.dw_part + ((size_t)item * BM + row) * p.K + cg * 64;
+                    float* dst = p.dw_part + (((size_t)b * p.MT + irow) * BM + row) * p.K + cg * 64;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         float v[32];
@@ -475,7 +513,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d2_empty);
+                if (lane == 0) arrive_lead(d2_empty);
                 if (p.db_part && c_row < p.M) p.db_part[((size_t)b * 4 + cg) * p.Mpad + c_row] = dsum;
             }
         }
@@ -484,7 +522,11 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) pair_sync();      // neither CTA leaves (or frees its TMEM) while the other may still signal it or read its shared memory
+    if (warp == 2) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
 }
 
 // per-(sample, joint) and per-(sample, channel) constants of the backward epilogues: one tiny launch
@@ -552,10 +594,39 @@ size_t head_bwd_workspace_bytes(int B, int K, int J, int D, int H, int W) {
     return n + 256;
 }
 
+// one CTA per SM (persistent), or one CTA PAIR per two SMs: a cluster of 2 running tcgen05.mma.cta_group::2
+template <bool DX, bool PAIR>
+static const char* launch_k4(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mb2, const CUtensorMap& mdx, const k4::Params& p, int items,
+                             int num_sms, cudaStream_t s) {
+    using namespace k4;
+    auto kern = head_bwd_kernel<DX, PAIR>;
+    const size_t smem = SMEM_BYTES + 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (head_bwd_kernel)";
+    cudaLaunchConfig_t cfg = {};
+    const int units = PAIR ? num_sms / 2 : num_sms;
+    const int g = items < units ? items : units;
+    cfg.gridDim = dim3((unsigned)(PAIR ? 2 * g : g));
+    cfg.blockDim = dim3(32 * (4 + EPI_WARPS));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, ma, mb1, mb2, mdx, p) != cudaSuccess) return "head_bwd_kernel launch failed";
+    return nullptr;
+}
+
+// pairs: 0 = never, 1 = the dX kernel on SM pairs (default when C_in is 128 or 256), 3 = the dW kernel too (experiment: 5 pair-items per
+// sample of 9 channel tiles quantise badly over 74 SM pairs)
 const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, const float* coords,
                                    const float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out,
-                                   void* dx_nhwc, float* dweight, float* dbias, void* workspace, int num_sms, int* launches, cudaStream_t s) {
+                                   void* dx_nhwc, float* dweight, float* dbias, void* workspace, int num_sms, int pairs, int* launches, cudaStream_t s) {
     using namespace k4;
+    if ((K / BK) % 2 != 0 || num_sms < 2) pairs = 0;         // the pair splits C_in in two halves of whole 64-channel blocks
     Params p;
     p.B = B; p.K = K; p.J = J; p.D = D; p.H = H; p.W = W;
     p.M = J * D;
@@ -605,13 +676,10 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
         !tc::make_map(&map_x64, x_nhwc, xrows, (uint64_t)K, 64))
         return "cuTensorMapEncodeTiled failed for the activations";
     if (dx_nhwc && !tc::make_map(&map_dx, dx_nhwc, xrows, (uint64_t)K, 32)) return "cuTensorMapEncodeTiled failed for d loss / d x";
-    const size_t smem = SMEM_BYTES + 1024;
     if (dweight || dbias) {
-        auto kern = head_bwd_kernel<false>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (K4w)";
-        int grid = B * p.MT;
-        if (grid > num_sms) grid = num_sms;
-        kern<<<grid, 32 * (4 + EPI_WARPS), smem, s>>>(map_w128, map_x256, map_x64, map_dx, p);
+        const char* err = (pairs & 2) ? launch_k4<false, true>(map_w128, map_x128, map_x64, map_dx, p, B * ((p.MT + 1) / 2), num_sms, s)
+                                      : launch_k4<false, false>(map_w128, map_x256, map_x64, map_dx, p, B * p.MT, num_sms, s);
+        if (err) return err;
         ++*launches;
 #ifdef IHPR_TIMING_EXPERIMENTS
         if (p.trace && getenv("IHPR_K4_TRACE")[0] == '2') {        // dump once: stamps relative to the first, per tile
@@ -638,11 +706,9 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
         ++*launches;
     }
     if (dx_nhwc) {
-        auto kern = head_bwd_kernel<true>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (K4x)";
-        int grid = B * p.PT;
-        if (grid > num_sms) grid = num_sms;
-        kern<<<grid, 32 * (4 + EPI_WARPS), smem, s>>>(map_x128, map_w256, map_w64, map_dx, p);
+        const char* err = (pairs & 1) ? launch_k4<true, true>(map_x128, map_w128, map_w64, map_dx, p, B * (p.PT / 2), num_sms, s)
+                                      : launch_k4<true, false>(map_x128, map_w256, map_w64, map_dx, p, B * p.PT, num_sms, s);
+        if (err) return err;
         ++*launches;
     }
     return nullptr;

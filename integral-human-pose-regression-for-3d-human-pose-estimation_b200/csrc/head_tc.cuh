@@ -1,5 +1,5 @@
-// head_tc.cuh -- tcgen05 / TMEM / TMA building blocks shared by the fused-head kernels (K3 / K4 in head_fused_fwd.cu, their
-// SM-pair form in head_fused_pair.cu): TMA tile loads / stores, UMMA descriptors and issue (cta_group::1 and ::2), TMEM
+// head_tc.cuh -- tcgen05 / TMEM / TMA building blocks shared by the fused-head kernels (K3 / K4 in head_fused_fwd.cu, K4w / K4x and
+// their SM-pair form in head_fused_bwd.cu): TMA tile loads / stores, UMMA descriptors and issue (cta_group::1 and ::2), TMEM
 // loads, packed fp32x2 math, tensor-map encoding.  sm_100a only.
 #pragma once
 #include <cuda.h>

@@ -343,10 +343,6 @@ const char* launch_head_fused(const void* x_nhwc, const void* w, const float* bi
 size_t head_bwd_workspace_bytes(int B, int K, int J, int D, int H, int W);
 const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, const float* coords,
                                    const float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out,
-                                   void* dx_nhwc, float* dweight, float* dbias, void* workspace, int num_sms, int* launches, cudaStream_t s);
-
-const char* launch_head_fused_pair(const void* x_nhwc, const void* w, const float* bias, int B, int K, int J, int D, int H, int W, float* coords,
-                                   float* stats, const float* gt, const float* vis, const float* have_depth, const float* grad_out, void* grad_heat,
-                                   float* dbias_part, int num_sms, cudaStream_t s);
+                                   void* dx_nhwc, float* dweight, float* dbias, void* workspace, int num_sms, int pairs, int* launches, cudaStream_t s);
 
 }  // namespace ihpr

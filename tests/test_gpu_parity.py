@@ -450,8 +450,9 @@ def test_fused_head_training_step(case, variant, dev):
     print("fused head backward variant %d %s: %s" % (variant, case, errs))
 
 
+@pytest.mark.parametrize("variant", [0, 3])     # 0: one CTA per SM; 3: both kernels on SM pairs (tcgen05.mma.cta_group::2, opt-in) where C_in allows
 @pytest.mark.parametrize("case", HEAD_CASES)
-def test_fused_head_backward_kernels_direct(case, dev):
+def test_fused_head_backward_kernels_direct(case, variant, dev):
     """ihpr_head_integral_l1_bwd_params through the C-ABI: partial requests (only dX, only dW + dbias) give the same bits as the full
     call, two runs are bit-identical (fixed-order batch reduction, no atomics), and the results match the fp64 truth."""
     import ihpr_b200
@@ -468,6 +469,7 @@ def test_fused_head_backward_kernels_direct(case, dev):
     L = lib()
     nbytes = L.ihpr_head_bwd_workspace_bytes(B, K, J, D, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ihpr_b200.set_variant(variant)
 
     def run(want_x, want_w, want_b):
         dx = torch.full((B, H, W, K), float("nan"), dtype=torch.bfloat16, device=dev) if want_x else None
@@ -494,38 +496,6 @@ def test_fused_head_backward_kernels_direct(case, dev):
     assert (dxl - dx64).abs().max().item() <= 6e-3 * dx64.abs().max().item()
     assert (dw.double().cpu() - dw64).abs().max().item() <= 4e-3 * dw64.abs().max().item()
     assert (db.double().cpu() - db64).abs().max().item() <= 1e-4 * db64.abs().max().item() + 1e-7
-
-
-@pytest.mark.parametrize("case", [(2, 18, 64, 256, 64, 64), (3, 17, 64, 256, 64, 64), (5, 5, 32, 128, 32, 32), (1, 3, 128, 192, 16, 32),
-                                  (90, 2, 32, 64, 8, 32)])
-def test_sm_pair_form_of_the_fused_head_is_bit_identical(case, dev):
-    """variant 5 = K3 / K4 on SM pairs (tcgen05 cta_group::2, csrc/head_fused_pair.cu): same tiles, same k order, same epilogues
-    as the single-SM kernels, so coordinates, statistics, the bf16 heat-map gradient and the bias partials must be bit-identical
-    (odd numbers of channel tiles leave a dead CTA in the last pair; J = 17 a partial tile; B = 90 more pair-items than pairs)."""
-    import ihpr_b200
-    from ihpr_b200._lib import lib, check
-    B, J, D, K, H, W = case
-    g = torch.Generator(device="cpu").manual_seed(B)
-    x = torch.randn(B, K, H, W, generator=g).to(torch.bfloat16).to(dev).contiguous(memory_format=torch.channels_last)
-    wb = (torch.randn(J * D, K, generator=g) * 0.05).to(torch.bfloat16).to(dev)
-    bias = (torch.randn(J * D, generator=g) * 0.5).to(dev)
-    gt = (torch.rand(B, J, 3, generator=g) * torch.tensor([W, H, D], dtype=torch.float32)).to(dev)
-    vis, hd, go = torch.ones(B, J, device=dev), torch.ones(B, 1, device=dev), torch.full((), 1.5, device=dev)
-    res = {}
-    for v in (0, 5):
-        ihpr_b200.set_variant(v)
-        with torch.no_grad():
-            coords, stats = ihpr_b200.functional.fused_head_soft_argmax(x, wb, bias, J, return_stats=True)
-        dheat = torch.full((B, J * D, H * W), float("nan"), dtype=torch.bfloat16, device=dev)
-        dbp = torch.full((B, 4, J * D), float("nan"), device=dev)
-        with torch.cuda.device(dev):
-            check(lib().ihpr_head_integral_l1_bwd(x.data_ptr(), wb.data_ptr(), bias.data_ptr(), B, K, J, D, H, W, coords.data_ptr(), stats.data_ptr(),
-                                                  gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), go.data_ptr(), dheat.data_ptr(), dbp.data_ptr(),
-                                                  torch.cuda.current_stream(dev).cuda_stream))
-        torch.cuda.synchronize()
-        res[v] = (coords, stats, dheat, dbp)
-    for a, b in zip(res[0], res[5]):
-        assert not torch.isnan(b.float()).any() and torch.equal(a, b)
 
 
 def test_deferred_heatmap_runs_the_reference_call_sequences(dev):

@@ -13,7 +13,7 @@ ap.add_argument("--D", type=int, default=64)
 ap.add_argument("--K", type=int, default=256)
 ap.add_argument("--hw", type=int, default=64)
 ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--variant", type=int, default=0, help="5 = SM-pair (cta_group::2) form of K3 / K4")
+ap.add_argument("--variant", type=int, default=0, help="3 = K4w / K4x on SM pairs (tcgen05 cta_group::2)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 ihpr_b200.set_variant(a.variant)

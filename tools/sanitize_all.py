@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K5, K5c with
-clusters of 2 / 8 / 16, K3 / K4 single-SM and SM-pair, K6) with finiteness checks: a quick all-kernel smoke on a B200, and the
+clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6) with finiteness checks: a quick all-kernel smoke on a B200, and the
 driver to put under `compute-sanitizer --tool memcheck|racecheck|synccheck` where the pool allows it (round 1's pool does not)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,8 +40,8 @@ loss_step(10, 18, 32, 32, 32, torch.float32, True, variant=7)      # K5c, cluste
 loss_step(4, 18, 64, 64, 64, torch.float32, True, variant=7)       # K5c, clusters of 16
 loss_step(6, 18, 64, 64, 64, torch.bfloat16, True, variant=7)      # K5c, clusters of 8
 loss_step(6, 18, 64, 64, 64, torch.float32, True)                  # K5, S = 12
-# K3 / K4 (single SM and SM pair)
-for v in (0, 5):
+# K3 forward + K4w / K4x backward (one CTA per SM, and both backward kernels on SM pairs)
+for v in (0, 3):
     ihpr_b200.set_variant(v)
     B, J, D, K, H, W = 3, 5, 32, 128, 32, 32
     x = torch.randn(B, K, H, W, generator=g).to(torch.bfloat16).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
