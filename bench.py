@@ -245,6 +245,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if not args.no_train:
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")        # PyTorch's recipe for capturing DDP's NCCL work (train.cuda_graph)
         dist.init_process_group("nccl", device_id=dev)
 
     B, J, D, W = args.batch, args.joints, args.depth, args.hw
@@ -334,7 +336,10 @@ def run_b200(args):
         torch.cuda.synchronize()
     clocks = sampler.stop()
     clocks["window"] = "timed region + 1 s continuation of the same step loop"
+    props = torch.cuda.get_device_properties(local)
     per_rank = gather_list({"rank": rank, "launch_ms": fwd_ms, "step_ms": total_ms / K, "k1_ms": k1_ms, "k2_ms": k2_ms, "path_choice": choice,
+                            "sms": props.multi_processor_count, "l2_bytes": getattr(props, "L2_cache_size", None),
+                            "power_w_max": clocks.get("power_w_max"),
                             "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}, world)
     if world > 1:
         t = torch.tensor([total_ms, fwd_ms, autograd_ms, k1_ms, k2_ms], device=dev, dtype=torch.float64)
@@ -600,11 +605,26 @@ def train_core(args, dev, world, rank, resnet, fused_head, crit_kind, cuda_graph
 
 
 def train_record(args, dev, world, rank):
-    """The `train` sub-record of the default bench line: BASELINE.json configs[1] (N=1) / configs[2] (N>1)."""
+    """The `train` sub-record of the default bench line: BASELINE.json configs[1] (N=1) / configs[2] (N>1).  The primary numbers are
+    the eager step (what main/train.py does: ~1200 launches per step); `cuda_graph` adds the same step replayed as ONE CUDA graph
+    (Trainer.capture(): forward, fused-head loss, backward with DDP's bucketed NCCL all-reduce, fused Adam), which is what removes the
+    host from the step -- it matters most at N = 8, where eight launch-bound processes share the box's cores."""
+    import gc
+    import torch
     a = argparse.Namespace(**vars(args))
     a.precision = "bf16"
-    return train_core(a, dev, world, rank, resnet=50, fused_head=True, crit_kind="head", cuda_graph=False,
-                      steps=args.train_steps, warmup=5)
+    rec = train_core(a, dev, world, rank, resnet=50, fused_head=True, crit_kind="head", cuda_graph=False,
+                     steps=args.train_steps, warmup=5)
+    gc.collect()
+    torch.cuda.empty_cache()
+    try:
+        g = train_core(a, dev, world, rank, resnet=50, fused_head=True, crit_kind="head", cuda_graph=True,
+                       steps=args.train_steps, warmup=5)
+        rec["cuda_graph"] = {"value": g["value"], "unit": g["unit"], "ms_per_step": g["ms_per_step"],
+                             "roofline_frac": g["roofline"]["frac"], "e2e_value": g["e2e"]["value"]}
+    except Exception as e:      # noqa: the eager record stands on its own
+        rec["cuda_graph"] = {"error": repr(e)[:300]}
+    return rec
 
 
 def run_train(args):

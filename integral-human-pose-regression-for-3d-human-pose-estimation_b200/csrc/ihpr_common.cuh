@@ -196,6 +196,56 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// release at cluster scope: the stores above are visible to whoever acquires this barrier's phase
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#ifdef IHPR_DEBUG_HANG
+    for (unsigned long long spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1ull << 22)) {
+            printf("HANG (cluster exchange) cta %d lane %d parity %u\n", blockIdx.x, threadIdx.x & 31, parity);
+            __trap();
+        }
+    }
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
+}
+
 // 16 B loads / stores
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
     uint4 r;
@@ -312,6 +362,7 @@ __device__ __forceinline__ uint64_t range_lo(uint64_t Gt, uint32_t G, uint32_t c
 __device__ __forceinline__ uint32_t owner_of(uint64_t g, uint64_t Gt, uint32_t G) { return (uint32_t)(((g + 1) * G - 1) / Gt); }
 
 void launch_fwd(const FwdParams& p, int dtype, bool vec_ok, int variant, int num_sms, cudaStream_t s);
+int fwd_cluster_size(const Geometry& g, int dtype);      // K1c: CTAs per joint-volume for a small batch, 0 = use the persistent ring kernel
 void launch_bwd(const BwdParams& p, int dtype, bool vec_ok, int variant, int num_sms, cudaStream_t s);
 Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok, int variant);
 int fused_split(const Geometry& g, int dtype);

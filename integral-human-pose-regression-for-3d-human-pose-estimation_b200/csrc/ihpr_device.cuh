@@ -6,38 +6,10 @@
 
 namespace ihpr {
 
-// ---------------------------------------------------------------------------------------------
-// Joint-volume finalisation.
-//
-// publish_row: called by ONE warp that holds this CTA's partial `b` of joint-volume r.  If other CTAs
-// also hold pieces of r, the partial goes to this CTA's fixed workspace slot and the last arriver
-// (atomic ticket) merges all slots in slot order; the winner writes coords / stats / loss term.
-__device__ __forceinline__ void publish_row(const FwdParams& p, int r, Acc b, int lane, uint32_t cta, uint32_t G) {
+// The merged partial `b` of joint-volume r is complete (held by every lane of ONE warp): coords / stats / loss term, and the
+// loss.py:52 mean once the last joint-volume of the launch has been finalised.
+__device__ __forceinline__ void finalize_row(const FwdParams& p, int r, const Acc& b, int lane) {
     const Geometry& g = p.g;
-    const uint64_t g0 = (uint64_t)r * g.nch;
-    const uint32_t c_first = owner_of(g0, g.Gt, G);
-    const uint32_t c_last = owner_of(g0 + g.nch - 1, g.Gt, G);
-    const int ncontrib = (int)(c_last - c_first) + 1;
-    bool last = true;
-    if (ncontrib > 1) {
-        int ticket = 0;
-        if (lane == 0) {
-            partial_to_global(p.partials + ((size_t)r * p.maxslots + (cta - c_first)) * 8, b);
-            __threadfence();
-            ticket = atomicAdd(p.row_count + r, 1);
-        }
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        last = (ticket == ncontrib - 1);
-        if (last) {
-            __threadfence();
-            b.reset();
-            const float* base = p.partials + (size_t)r * p.maxslots * 8;
-            for (int s = lane; s < ncontrib; s += 32) b = acc_merge(b, partial_from_global(base + s * 8));
-            b = acc_warp_merge(b);
-            if (lane == 0) p.row_count[r] = 0;      // leave the workspace zeroed for the next launch
-        }
-    }
-    if (!last) return;
     const float inv = 1.0f / b.l;
     const float cx = b.sx * inv, cy = b.sy * inv, cz = b.sz * inv;
     int t2 = 0;
@@ -72,6 +44,42 @@ __device__ __forceinline__ void publish_row(const FwdParams& p, int r, Acc b, in
             if (lane == 0) { p.loss[0] = s / (float)g.R; *p.done_rows = 0; }
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Joint-volume finalisation.
+//
+// publish_row: called by ONE warp that holds this CTA's partial `b` of joint-volume r.  If other CTAs
+// also hold pieces of r, the partial goes to this CTA's fixed workspace slot and the last arriver
+// (atomic ticket) merges all slots in slot order; the winner writes coords / stats / loss term.
+__device__ __forceinline__ void publish_row(const FwdParams& p, int r, Acc b, int lane, uint32_t cta, uint32_t G) {
+    const Geometry& g = p.g;
+    const uint64_t g0 = (uint64_t)r * g.nch;
+    const uint32_t c_first = owner_of(g0, g.Gt, G);
+    const uint32_t c_last = owner_of(g0 + g.nch - 1, g.Gt, G);
+    const int ncontrib = (int)(c_last - c_first) + 1;
+    bool last = true;
+    if (ncontrib > 1) {
+        int ticket = 0;
+        if (lane == 0) {
+            partial_to_global(p.partials + ((size_t)r * p.maxslots + (cta - c_first)) * 8, b);
+            __threadfence();
+            ticket = atomicAdd(p.row_count + r, 1);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        last = (ticket == ncontrib - 1);
+        if (last) {
+            __threadfence();
+            b.reset();
+            const float* base = p.partials + (size_t)r * p.maxslots * 8;
+            for (int s = lane; s < ncontrib; s += 32) b = acc_merge(b, partial_from_global(base + s * 8));
+            b = acc_warp_merge(b);
+            if (lane == 0) p.row_count[r] = 0;      // leave the workspace zeroed for the next launch
+        }
+    }
+    if (!last) return;
+    finalize_row(p, r, b, lane);
 }
 
 // Barrier flavour (direct / scalar kernels): all NW warps meet, warp 0 merges and publishes.

@@ -26,55 +26,6 @@ namespace {
 
 constexpr int kMaxCluster = 16;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory object in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// release at cluster scope: the stores above are visible to whoever acquires this barrier's phase
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-#ifdef IHPR_DEBUG_HANG
-    for (unsigned long long spins = 0;; ++spins) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-        if (spins > (1ull << 22)) {
-            printf("HANG (cluster exchange) cta %d lane %d parity %u\n", blockIdx.x, threadIdx.x & 31, parity);
-            __trap();
-        }
-    }
-#else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-#endif
-}
-
 // Roles: warp 0 = TMA producer, warps 1..NCW = consumers, warp NCW+1 = exchanger.
 // The CTA's chunks form one stream t = u*C + j (u-th volume of the cluster, j-th chunk of this CTA's slice).  Consumers
 // alternate P1(t), P2(t - L): pass 2 trails pass 1 by L >= C chunks, so L stages hold data between the passes and the other

@@ -15,6 +15,8 @@
 //                   mbarrier full/empty pairs), NCW consumer warps read the ring with 128-bit LDS.
 //   direct kernel : every thread issues U 128-bit streaming global loads per step (also the scalar
 //                   fallback for shapes with W % 4 != 0 or unaligned bases).
+#include <cstdlib>
+
 #include "ihpr_device.cuh"
 
 namespace ihpr {
@@ -190,6 +192,77 @@ __global__ void __launch_bounds__(NT) fwd_scalar_kernel(const FwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1c -- small batches (inference at cfg.test_batch_size = 4, /root/reference/main/config.py:44, main/test.py:53-65): a handful of
+// joint-volumes must still fill 148 SMs, so every volume is split over the CS CTAs of a thread-block CLUSTER and the CS partials meet in
+// the leader's shared memory (st.shared::cluster + a remote mbarrier arrive) instead of the global-memory publish -> ticket -> last-CTA
+// merge chain of the persistent kernels (4-5 dependent L2 round trips, ~4.6 of K1's 14 us at B = 1).  Data this small is L2-resident
+// on repeated calls, so plain 128-bit loads replace the TMA ring (no pipeline to fill).  Merge order = cluster rank: bit-reproducible.
+template <typename T, int NT, int U>
+__global__ void __launch_bounds__(NT, 1) fwd_cluster_kernel(const FwdParams p) {
+    __shared__ float red[NT / 32][8];
+    __shared__ __align__(16) float xpart[8][8];         // leader: partial of cluster rank q
+    __shared__ uint64_t xbar;
+    const Geometry& g = p.g;
+    const uint32_t CS = cluster_nctarank(), q = cluster_ctarank();
+    const uint32_t cid = blockIdx.x / CS, ncl = gridDim.x / CS;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(&xbar, CS); mbar_fence_init(); }
+    __syncthreads();
+    cluster_sync_all();             // the leader's barrier exists before anybody arrives on it
+    constexpr int QPV = Elem<T>::QPV;
+    constexpr int VPC = NT * U;     // vectors per full chunk (the geometry's 32 KiB chunks)
+    const uint32_t k0 = (uint32_t)((uint64_t)g.nch * q / CS), k1 = (uint32_t)((uint64_t)g.nch * (q + 1) / CS);
+    const bool fast = fast_ok<NT, VPC>(g);
+    const uint32_t Fv = fast ? g.divFv.d : 1;
+    const float x0f = u2f((uint32_t)(tid % Fv) * (4 * QPV)), rsf = u2f(NT / Fv), hf = u2f((uint32_t)g.H);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.heat);
+    uint32_t seq = 0;
+    for (uint32_t r = cid; r < (uint32_t)g.R; r += ncl, ++seq) {
+        Acc a;
+        a.reset();
+        uint64_t w2 = 0;
+        for (uint32_t k = k0; k < k1; ++k) {
+            const uint32_t e0 = k * g.CE;
+            const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
+            const uint8_t* cp = src + ((size_t)r * g.N + e0) * sizeof(T);
+            auto load = [&](uint32_t iv) { return ld_stream16(cp + (size_t)iv * 16); };
+            if (fast) {
+                if (n_vec == VPC) consume_chunk_fast_pk<T, U, NT, VPC, true>(a, w2, g, n_vec, k * VPC, tid, rsf, hf, load);
+                else consume_chunk_fast_pk<T, U, NT, VPC, false>(a, w2, g, n_vec, k * VPC, tid, rsf, hf, load);
+            } else {
+                consume_chunk<T, U, NT>(a, g, n_vec, e0 >> 2, tid, load);
+            }
+        }
+        if (fast) { fold_w2(a, w2); a.sx = fmaf(x0f, a.l, a.sx); }
+        a = acc_warp_merge(a);
+        if (lane == 0) partial_to_smem(red[wid], a);
+        __syncthreads();
+        if (wid == 0) {
+            Acc b;
+            b.reset();
+            if (lane < NT / 32) b = partial_from_smem(red[lane]);
+            b = acc_warp_merge(b);
+            if (lane == 0) {        // this CTA's partial -> slot q of the leader, then one arrival on the leader's barrier
+                const uint32_t dst = map_to_cta(&xpart[q][0], 0);
+                st_cluster_f4(dst, b.m, b.l, b.sx, b.sy);
+                st_cluster_f4(dst + 16, b.sz, b.mx, 0.f, 0.f);
+                mbar_arrive_remote(map_to_cta(&xbar, 0));
+            }
+            if (q == 0) {
+                mbar_wait_cluster(&xbar, seq & 1);
+                Acc t;
+                t.reset();
+                if (lane < (int)CS) t = partial_from_smem(xpart[lane]);
+                t = acc_warp_merge(t);
+                finalize_row(p, (int)r, t, lane);
+            }
+        }
+        // the leader has read xpart (and every CTA is done with red[]) before the next joint-volume's partials arrive
+        cluster_sync_all();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <typename T, int CHUNK_BYTES, int STAGES, int NCW, int MINB>
 static void launch_ring(const FwdParams& p, int num_sms, cudaStream_t s) {
     auto kern = fwd_ring_kernel<T, CHUNK_BYTES, STAGES, NCW, MINB>;
@@ -245,9 +318,66 @@ Geometry make_geometry(int B, int J, int D, int H, int W, int dtype, bool vec_ok
     return g;
 }
 
+// K1c launch: R clusters of CS CTAs (R joint-volumes, one cluster each; fewer clusters than volumes never happens here)
+template <typename T>
+static bool launch_cluster(const FwdParams& p, int CS, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.g.R * CS));
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, fwd_cluster_kernel<T, 512, 4>, p) == cudaSuccess) return true;
+    (void)cudaGetLastError();
+    return false;
+}
+
+// how many clusters of CS CTAs of K1c the device holds at once (cached; 0 = cannot launch)
+template <typename T>
+static int cluster_capacity(int CS) {
+    static int cache[9] = {0};
+    if (cache[CS] == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(CS * 64));
+        cfg.blockDim = dim3(512);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fwd_cluster_kernel<T, 512, 4>, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        cache[CS] = 1 + n;
+    }
+    return cache[CS] - 1;
+}
+
+// CTAs per joint-volume for K1c, 0 = use the persistent ring kernel.  Measured (profiles/r02_kbench_small.txt, J = 18, 64^3): clusters
+// of 4 win while all of them are resident at once (B = 1: 12.4 vs 14.2 us fp32, 11.0 vs 12.4 us bf16); pairs win for bf16 up to one pair
+// per SM pair (B = 4: 15.3 vs 18.5 us) and lose for fp32 (B = 2: 20.3 vs 16.5 us -- 72 CTAs with plain loads stream less than 148 with the
+// TMA ring); beyond that every SM streams plenty in the persistent kernels and their tail is amortised.
+int fwd_cluster_size(const Geometry& g, int dtype) {
+    if (getenv("IHPR_NO_K1C")) return 0;
+    if (g.nch >= 4 && g.R <= (dtype == 0 ? cluster_capacity<float>(4) : cluster_capacity<__nv_bfloat16>(4))) return 4;
+    if (dtype != 0 && g.nch >= 2 && g.R <= cluster_capacity<__nv_bfloat16>(2)) return 2;
+    return 0;
+}
+
 template <typename T>
 static void launch_fwd_t(const FwdParams& p, bool vec_ok, int variant, int num_sms, cudaStream_t s) {
     if (!vec_ok) return launch_scalar<T>(p, num_sms, s);
+    if (variant == 0) {             // auto: small batches go to the cluster kernel
+        const int CS = fwd_cluster_size(p.g, sizeof(T) == 4 ? 0 : 1);
+        if (CS && launch_cluster<T>(p, CS, s)) return;
+    }
     switch (variant) {
         case 2: return launch_direct<T, 512, 4, 2>(p, num_sms, s);
         case 21: return launch_direct<T, 256, 4, 4>(p, num_sms, s);

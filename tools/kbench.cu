@@ -75,6 +75,12 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1); const double tf = ms * 1e3 / iters;
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(bwd()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tb = ms * 1e3 / iters;
+    // inference call (main/test.py:53-65): coordinates only, no statistics, no loss
+    auto inf = [&] { return ihpr_softargmax3d_fwd(heat, dtype, B, J, D, H, W, coords, nullptr, ws, wsb, nullptr); };
+    for (int i = 0; i < 3; ++i) IK(inf());
+    cudaEventRecord(e0); for (int i = 0; i < iters; ++i) IK(inf()); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms, e0, e1); const double ti = ms * 1e3 / iters;
+    IK(fwd());      // restore coords / stats / loss of the training forward for what follows
     cudaEventRecord(e0); for (int i = 0; i < iters; ++i) { IK(fwd()); IK(bwd()); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1); const double tfb = ms * 1e3 / iters;
     if (verbose) { printf("K1/K2 timing done\n"); fflush(stdout); }
@@ -108,7 +114,7 @@ int main(int argc, char** argv) {
     const double V = (double)R * N * es;
     printf("variant %d B %d dtype %d: FUSED one-launch fwd+bwd %.1f us (%d launch; %.0f GB/s as 3V, %.0f GB/s as 2V, %.0f vol/s)\n", variant, B, dtype, tfu,
            ihpr_last_launch_count(), 3 * (double)R * N * es / tfu / 1e3, 2 * (double)R * N * es / tfu / 1e3, R / (tfu * 1e-6));
-    printf("variant %d B %d dtype %d: fwd %.1f us (%.0f GB/s)  bwd %.1f us (%.0f GB/s)  fwd+bwd %.1f us (%.0f GB/s, %.0f vol/s)  loss %.5f\n", variant, B, dtype,
-           tf, V / tf / 1e3, tb, 2 * V / tb / 1e3, tfb, 3 * V / tfb / 1e3, R / (tfb * 1e-6), hl);
+    printf("variant %d B %d dtype %d: fwd %.1f us (%.0f GB/s)  inference fwd %.1f us  bwd %.1f us (%.0f GB/s)  fwd+bwd %.1f us (%.0f GB/s, %.0f vol/s)  loss %.5f\n", variant, B, dtype,
+           tf, V / tf / 1e3, ti, tb, 2 * V / tb / 1e3, tfb, 3 * V / tfb / 1e3, R / (tfb * 1e-6), hl);
     return 0;
 }
