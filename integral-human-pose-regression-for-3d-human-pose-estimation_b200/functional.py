@@ -417,7 +417,7 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
             check(lib().ihpr_integral_l1_from_coords(coords.data_ptr(), gt.data_ptr(), vis.data_ptr(), hd.data_ptr(), B, J, loss.data_ptr(), stream))
         ctx.save_for_backward(xb, wb, bf, coords, stats, gt, vis, hd)
         ctx.variant = lib().ihpr_get_variant()
-        ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape))
+        ctx.meta = (x.dtype, weight.dtype, bias.dtype, tuple(weight.shape), tuple(weight.stride()))
         ctx.mark_non_differentiable(coords)
         ctx.set_materialize_grads(False)
         return loss, coords
@@ -427,7 +427,7 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         if grad_loss is None:
             return None, None, None, None, None, None
         xb, wb, bf, coords, stats, gt, vis, hd = ctx.saved_tensors
-        x_dtype, w_dtype, b_dtype, w_shape = ctx.meta
+        x_dtype, w_dtype, b_dtype, w_shape, w_stride = ctx.meta
         B, K, H, W = xb.shape
         M, J = wb.shape[0], gt.shape[1]
         N = H * W
@@ -446,6 +446,8 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
             xn = xb.permute(0, 2, 3, 1).reshape(B, N, K)                              # view of the channels_last activations
             dx = torch.matmul(dheat.transpose(1, 2), wb).view(B, H, W, K).permute(0, 3, 1, 2).to(x_dtype) if need_x else None
             dw = torch.bmm(dheat, xn, out_dtype=torch.float32).sum(0).view(w_shape).to(w_dtype) if need_w else None
+            if dw is not None and len(w_shape) == 4 and w_shape[2:] == (1, 1):
+                dw = torch.as_strided(dw, w_shape, w_stride)
             db = db_part.sum(dim=(0, 1)).to(b_dtype) if need_b else None
             return dx, dw, db, None, None, None
         # K4w / K4x: dW, dbias and dX straight out of the tensor-core kernels; neither the heat-map nor its gradient is ever stored
@@ -464,7 +466,10 @@ class _FusedHeadIntegralL1(torch.autograd.Function):
         if dx is not None:
             dx = dx.permute(0, 3, 1, 2).to(x_dtype)                   # logical (B, K, H, W), channels_last strides, no copy for bf16 x
         if dw is not None:
-            dw = dw.view(w_shape).to(w_dtype)
+            # the gradient in the parameter's own strides (a channels_last (M, K, 1, 1) weight has strides (K, 1, K, K)): same memory,
+            # and DDP's bucket views then take it without a re-layout copy
+            dw = dw.to(w_dtype)
+            dw = torch.as_strided(dw, w_shape, w_stride) if len(w_shape) == 4 and w_shape[2:] == (1, 1) else dw.view(w_shape)
         if db is not None:
             db = db.to(b_dtype)
         return dx, dw, db, None, None, None
