@@ -219,7 +219,22 @@ def measure_pcie(dev, nbytes=256 << 20, reps=3):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         out.append(nbytes / (best * 1e-3) / 1e9)
-    return out[0], out[1]
+    # both directions at once (what the pipelined step does): two streams, each direction timed by its own events
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    h2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(s1):
+            ev[0].record(); d.copy_(h, non_blocking=True); ev[1].record()
+        with torch.cuda.stream(s2):
+            ev[2].record(); h2.copy_(d2, non_blocking=True); ev[3].record()
+        torch.cuda.synchronize()
+        best = min(best, max(ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])))
+    out.append(nbytes / (best * 1e-3) / 1e9)
+    return out[0], out[1], out[2]
 
 
 def gather_list(x, world):
@@ -351,7 +366,7 @@ def run_b200(args):
     # ---- e2e: same step through the host-buffer C-ABI entry point, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        h2d_gbs, d2h_gbs = measure_pcie(dev)
+        h2d_gbs, d2h_gbs, bidir_gbs = measure_pcie(dev)
         hh = torch.empty(heat.shape, dtype=dtype, pin_memory=True)
         hh.copy_(heat.detach())
         out = {"grad": torch.empty(heat.shape, dtype=dtype, pin_memory=True), "loss": torch.empty(1).pin_memory(),
@@ -376,12 +391,15 @@ def run_b200(args):
         small_in = (R * 3 + R + B + 1) * 4
         h2d_b, d2h_b = R * N * es + small_in, R * N * es + R * 3 * 4 + 4
         floor_ms = max(h2d_b / (h2d_gbs * 1e9), d2h_b / (d2h_gbs * 1e9)) * 1e3
+        floor_bidir_ms = max(h2d_b, d2h_b) / (bidir_gbs * 1e9) * 1e3
         e2e = {"value": world * R / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b,
                "d2h_bytes_per_step": d2h_b, "ms_per_step": e2e_s * 1e3, "steps": ke,
                "launches_per_step": e2e_launch, "slices": args.slices,
                "pcie_h2d_GBps": h2d_gbs, "pcie_d2h_GBps": d2h_gbs, "pcie_floor_ms": floor_ms,
+               "pcie_bidirectional_GBps_per_direction": bidir_gbs, "pcie_floor_bidirectional_ms": floor_bidir_ms,
                "pcie_floor_note": "bytes / this rank's pinned-copy bandwidth measured alone just before (the two directions overlap: the floor is the "
-                                  "slower one); with N ranks every GPU hangs off the same host memory, so ms_per_step_per_rank rises with N",
+                                  "slower one); pcie_floor_bidirectional_ms uses the per-direction rate with BOTH directions busy, which is what the "
+                                  "pipelined step sees; with N ranks every GPU hangs off the same host memory, so ms_per_step_per_rank rises with N",
                "ms_per_step_per_rank": e2e_ranks,
                "api": "ihpr_integral_l1_fwd_bwd_host (pinned host buffers, synchronous)"}
         del hh, out

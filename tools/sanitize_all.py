@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K5, K5c with
+"""tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K1c, K5, K5c with
 clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6) with finiteness checks: a quick all-kernel smoke on a B200, and the
 driver to put under `compute-sanitizer --tool memcheck|racecheck|synccheck` where the pool allows it (round 1's pool does not)."""
 import os, sys
@@ -33,6 +33,9 @@ for v in (0, 2):
     loss_step(2, 3, 8, 16, 16, torch.float32, False, v)
 loss_step(2, 3, 8, 16, 16, torch.bfloat16, False)
 loss_step(2, 2, 3, 5, 9, torch.float32, False)                     # scalar path
+loss_step(1, 18, 64, 64, 64, torch.float32, False)                 # K1c: clusters of 4 with a DSMEM merge (small batch)
+loss_step(4, 17, 64, 64, 64, torch.bfloat16, False)                # K1c: clusters of 2 (bf16)
+loss_step(2, 3, 8, 16, 16, torch.float32, False, 11)               # the persistent ring kernel on a small batch
 # K5 (cooperative, L2-resident) and K5c (cluster-resident), enough joint-volumes for the one-launch path
 loss_step(20, 16, 8, 16, 16, torch.float32, True)                  # 8 KiB volumes: S = 1
 loss_step(10, 18, 32, 32, 32, torch.float32, True)                 # 128 KiB volumes
