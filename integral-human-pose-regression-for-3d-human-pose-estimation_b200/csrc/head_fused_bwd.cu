@@ -72,7 +72,7 @@ struct Params {
     int CB;                 // ceil(M / 256)     (K4x: channel blocks per item)
     const float* k0tab;     // (B, Mpad): bias[c] * log2e - m[b, joint(c)] * log2e; -inf for c >= M (weight 0)
     const float4* jtab;     // (B, Jpad): {gx, gy, gz, -(gx cx + gy cy + gz cz)} with g pre-divided by l; zeros for joints >= J
-    float* dw_part;         // K4w out: (B * MT, 128, K) fp32 partial d loss / d weight per (sample, channel tile)
+    float* dw_part;         // K4w out: (B * MT, K, 128) fp32 partial d loss / d weight per (sample, channel tile), channel fastest
     float* db_part;         // K4w out: (B, 4, Mpad) fp32 partial d loss / d bias
     int dbg;                // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_K4_DEBUG): 1 = no GEMM2 operand loads, 2 = no epilogue math,
                             // 4 = no GEMM1 operand loads, 8 = no GEMM2 MMAs -- WRONG results, timing experiments only
@@ -498,17 +498,18 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // the next item's epilogue writes other rows / blocks of the staging buffer than this warp just stored from
                 named_bar_sync(1, EPI_WARPS * 32);
             } else {
-                // dW partial [128 channels x K] fp32 -> workspace, 256 contiguous bytes per thread and 64-column group
+                // dW partial [128 channels x K] fp32 -> workspace, TRANSPOSED ([K][128 channels]): a thread owns a channel (TMEM lane), so the 32
+                // lanes of a warp write 128 contiguous bytes per store.  (Row-major float4 stores put 16 bytes into each of 32 different
+                // lines per instruction: 8192 line transactions per drain, ~10 k clk -- profiles/r02_k4_ts_trace.txt.)
                 const bool warp_live = irow * BM + qd * 32 < p.M;     // 32 consecutive channels: live or dead together (M % 32 == 0)
                 if (cg < p.KB && warp_live) {
-                    float* dst = p.dw_part + (((size_t)b * p.MT + irow) * BM + row) * p.K + cg * 64;
+                    float* dst = p.dw_part + (((size_t)b * p.MT + irow) * p.K + cg * 64) * BM + row;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         float v[32];
                         tmem_ld32(tmem_base + lane_off + D2_COL + (uint32_t)(cg * 64 + q * 32), v);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4*>(dst + q * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < 32; ++i) dst[(size_t)(q * 32 + i) * BM] = v[i];
                     }
                 }
                 tc_fence_before();
@@ -558,16 +559,29 @@ __global__ void head_bwd_prep_kernel(const float* __restrict__ bias, const float
     }
 }
 
-// dW[c, k] = sum_b part[b, tile(c), c % 128, k]  and  dbias[c] = sum_b sum_g db_part[b, g, c]   -- fixed order: bit-reproducible
+// dW[c, k] = sum_b part[b, tile(c), k, c % 128]  and  dbias[c] = sum_b sum_g db_part[b, g, c]   -- fixed order: bit-reproducible.
+// The thread index runs over (tile, k, channel) like the partials, so the reads are coalesced; 4 independent partial sums keep
+// enough loads in flight (combined in a fixed order).
 __global__ void head_bwd_reduce_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int B, int M, int Mpad, int K, int MT,
                                        float* __restrict__ dw, float* __restrict__ dbias) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (dw && idx < M * K) {
-        const int c = idx / K, k = idx - c * K;
-        const int mt = c / BM, r = c - mt * BM;
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += __ldg(dw_part + (((size_t)b * MT + mt) * BM + r) * K + k);
-        dw[idx] = s;
+    if (dw && idx < MT * BM * K) {
+        const int r = idx % BM, k = (idx / BM) % K, mt = idx / (BM * K);
+        const int c = mt * BM + r;
+        if (c < M) {
+            const size_t stride = (size_t)MT * K * BM;
+            const float* src = dw_part + ((size_t)mt * K + k) * BM + r;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int b = 0;
+            for (; b + 4 <= B; b += 4) {
+                s0 += __ldg(src + (size_t)b * stride);
+                s1 += __ldg(src + (size_t)(b + 1) * stride);
+                s2 += __ldg(src + (size_t)(b + 2) * stride);
+                s3 += __ldg(src + (size_t)(b + 3) * stride);
+            }
+            for (; b < B; ++b) s0 += __ldg(src + (size_t)b * stride);
+            dw[(size_t)c * K + k] = (s0 + s1) + (s2 + s3);
+        }
     }
     if (dbias && idx < M) {
         float s = 0.f;
@@ -701,7 +715,7 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
             }
         }
 #endif
-        const int n = p.M * K, th = 256;
+        const int n = p.MT * BM * K, th = 256;
         head_bwd_reduce_kernel<<<(n + th - 1) / th, th, 0, s>>>(dw_part, db_part, B, p.M, p.Mpad, K, p.MT, dweight, dbias);
         ++*launches;
     }
