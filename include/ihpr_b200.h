@@ -200,6 +200,25 @@ int ihpr_head_integral_l1_bwd_params(const void *x_nhwc, const void *weight, con
                                      const float *grad_out, void *dx_nhwc, float *dweight, float *dbias,
                                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* The last block of HeadNet.deconv_layers at inference (main/model.py:22-38, the third ConvTranspose2d(256, 256, k4, s2, p1,
+ * bias=False) + BatchNorm2d in eval mode + ReLU, 32 x 32 -> 64 x 64) as one tensor-core kernel (csrc/deconv_bn_relu.cu): four
+ * sub-pixel phases, each a GEMM over 2 x 2 taps x C_in whose shifted A operand is a zero-filled TMA box of the input; BatchNorm
+ * folded to a per-channel scale / shift applied in fp32 to the accumulator, ReLU, bf16.
+ *   ihpr_deconv_bn_relu_prepare -- once per set of parameters (1 launch): re-lays the ConvTranspose2d weight (C_in, C_out, 4, 4)
+ *     bf16 contiguous into 16 K-major (phase, tap) planes and folds gamma / beta / running_mean / running_var (C_out fp32 each)
+ *     and eps into scale / shift, all inside `workspace` (ihpr_deconv_bn_relu_workspace_bytes bytes -- 2 MiB for 256 x 256 --
+ *     256-byte aligned, no initialisation needed);
+ *   ihpr_deconv_bn_relu -- per batch (1 launch): x_nhwc (B, Hin, Win, C_in) bf16 (the channels_last layout of (B, C_in, Hin, Win))
+ *     -> y_nhwc (B, 2 Hin, 2 Win, C_out) bf16, exactly the operand ihpr_head_softargmax_fwd reads; `prepared` is a workspace
+ *     ihpr_deconv_bn_relu_prepare filled on the same stream (or earlier).
+ * Needs C_out == 256, C_in % 64 == 0, Win == 32, Hin % 8 == 0.  Inference only (running statistics; no backward). */
+size_t ihpr_deconv_bn_relu_workspace_bytes(int Cin, int Cout);
+int ihpr_deconv_bn_relu_prepare(const void *weight, const float *gamma, const float *beta,
+                                const float *running_mean, const float *running_var, float eps,
+                                int Cin, int Cout, void *workspace, size_t workspace_bytes, void *stream);
+int ihpr_deconv_bn_relu(const void *x_nhwc, const void *prepared, int B, int Cin, int Cout, int Hin, int Win,
+                        void *y_nhwc, void *stream);
+
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in
  * `slices` batch slices pipelined over internal streams, runs forward + backward and copies

@@ -546,6 +546,59 @@ int ihpr_head_integral_l1_bwd_params(const void* x_nhwc, const void* weight, con
     return IHPR_OK;
 }
 
+size_t ihpr_deconv_bn_relu_workspace_bytes(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0) return 0;
+    return ihpr::deconv_workspace_bytes(Cin, Cout);
+}
+
+static int deconv_channel_check(int Cin, int Cout) {
+    if (Cin <= 0 || Cin % 64 != 0) return fail(IHPR_EINVAL, "deconv_bn_relu needs C_in a multiple of 64 (got %d)", Cin);
+    if (Cout != 256) return fail(IHPR_EINVAL, "deconv_bn_relu needs C_out == 256 (got %d)", Cout);
+    return IHPR_OK;
+}
+
+int ihpr_deconv_bn_relu_prepare(const void* weight, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                                int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!weight || !gamma || !beta || !running_mean || !running_var || !workspace) return fail(IHPR_EINVAL, "null argument");
+    int rc = deconv_channel_check(Cin, Cout);
+    if (rc) return rc;
+    if (!(eps >= 0.f)) return fail(IHPR_EINVAL, "eps must be non-negative");
+    if ((uintptr_t)weight & 15) return fail(IHPR_EINVAL, "weight must be 16-byte aligned");
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    const size_t need = ihpr::deconv_workspace_bytes(Cin, Cout);
+    if (workspace_bytes < need) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, need);
+    int num_sms = 0;
+    rc = check_device(weight, &num_sms);
+    if (rc) return rc;
+    int launches = 0;
+    ihpr::launch_deconv_prepare(weight, gamma, beta, running_mean, running_var, eps, Cin, Cout, workspace, &launches, static_cast<cudaStream_t>(stream));
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+int ihpr_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, void* stream) {
+    g_launches = 0;
+    if (!x_nhwc || !prepared || !y_nhwc) return fail(IHPR_EINVAL, "null argument");
+    if (B <= 0) return fail(IHPR_EINVAL, "non-positive batch");
+    int rc = deconv_channel_check(Cin, Cout);
+    if (rc) return rc;
+    if (Win != 32 || Hin <= 0 || Hin % 8 != 0) return fail(IHPR_EINVAL, "deconv_bn_relu needs an input of width 32 and a height that is a multiple of 8 (got %dx%d)", Hin, Win);
+    if ((long long)B * Hin > 0x7fffffffLL / 4) return fail(IHPR_EINVAL, "B*H does not fit");
+    if (((uintptr_t)x_nhwc | (uintptr_t)y_nhwc) & 15) return fail(IHPR_EINVAL, "x / y must be 16-byte aligned");
+    if ((uintptr_t)prepared & 255) return fail(IHPR_EINVAL, "the prepared workspace must be 256-byte aligned");
+    int num_sms = 0;
+    rc = check_device(x_nhwc, &num_sms);
+    if (rc) return rc;
+    int launches = 0;
+    const char* err = ihpr::launch_deconv_bn_relu(x_nhwc, prepared, B, Cin, Cout, Hin, Win, y_nhwc, num_sms, &launches, static_cast<cudaStream_t>(stream));
+    if (err) return fail(IHPR_ECUDA, "%s", err);
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
                                   const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
                                   int device, int slices) {

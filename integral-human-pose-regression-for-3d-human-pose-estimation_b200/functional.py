@@ -393,6 +393,47 @@ def fused_head_soft_argmax(x, weight, bias, joint_num, return_stats=False):
     return (coords, stats) if return_stats else coords
 
 
+def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
+    """relu(batch_norm(conv_transpose2d(x, weight, stride=2, padding=1))) with the BatchNorm in eval mode, as ONE tensor-core kernel
+    (K9, csrc/deconv_bn_relu.cu): the last deconv block of HeadNet at inference (main/model.py:22-38).  x: (B, C_in, H, 32) cuda
+    tensor (made bf16 / channels_last if it is not); weight: the ConvTranspose2d weight (C_in, 256, 4, 4).  Returns the
+    (B, 256, 2 H, 64) bf16 channels_last activation -- the operand fused_head_soft_argmax reads without a copy.  Forward only.
+    The re-laid weights and the folded BatchNorm are cached per (device, stream) until one of the parameter tensors changes
+    (storage or in-place version), so a steady inference loop is one launch per call."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or weight.dim() != 4 or tuple(weight.shape[2:]) != (4, 4) or weight.shape[0] != x.shape[1]:
+        raise ValueError("x must be (B, C_in, H, W) and weight (C_in, C_out, 4, 4), got %s / %s" % (tuple(x.shape), tuple(weight.shape)))
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise IhprError("deconv_bn_relu is forward-only (inference with running statistics); call it under torch.no_grad()")
+    B, Cin, H, W = x.shape
+    Cout = weight.shape[1]
+    dev = x.device
+    xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    params = (weight, bn_weight, bn_bias, running_mean, running_var)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream)
+        stamp = tuple((t.data_ptr(), t._version, t.dtype) for t in params) + (float(eps), Cin, Cout)
+        entry = _DECONV_PREPARED.get(key)
+        if entry is None or entry[0] != stamp:
+            nbytes = lib().ihpr_deconv_bn_relu_workspace_bytes(Cin, Cout)
+            if nbytes == 0:
+                raise IhprError("deconv_bn_relu: bad channel counts %d -> %d" % (Cin, Cout))
+            ws = entry[1] if entry is not None and entry[1].numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            wb = weight.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            g, b_, m, v = (t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in params[1:])
+            check(lib().ihpr_deconv_bn_relu_prepare(wb.data_ptr(), g.data_ptr(), b_.data_ptr(), m.data_ptr(), v.data_ptr(), float(eps), Cin, Cout,
+                                                    ws.data_ptr(), nbytes, stream))
+            entry = (stamp, ws)
+            _DECONV_PREPARED[key] = entry
+        y = torch.empty((B, Cout, 2 * H, 2 * W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        check(lib().ihpr_deconv_bn_relu(xb.data_ptr(), entry[1].data_ptr(), B, Cin, Cout, H, W, y.data_ptr(), stream))
+    return y
+
+
+_DECONV_PREPARED = {}
+
+
 class _FusedHeadIntegralL1(torch.autograd.Function):
     """final_layer (1x1 conv) + soft-argmax + L1 loss with the heat-map living only in TMEM: K3 forward; K4w / K4x backward
     (dW, dbias, dX in-kernel -- no heat-map gradient in HBM, no library GEMM).

@@ -10,7 +10,7 @@ sm_100a path (what main/train.py:64-67 does in two calls).
 import torch
 import torch.nn as nn
 
-from .functional import DeferredHeatmap, flip_merge, fused_head_integral_l1_loss, fused_head_soft_argmax
+from .functional import DeferredHeatmap, deconv_bn_relu, flip_merge, fused_head_integral_l1_loss, fused_head_soft_argmax
 from .nets.loss import JointLocationLoss, soft_argmax
 from .nets.resnet import ResNetBackbone
 
@@ -30,6 +30,18 @@ class HeadNet(nn.Module):
 
     def forward(self, x):
         return self.final_layer(self.deconv_layers(x))
+
+    def features(self, x):
+        """deconv_layers(x).  At inference (eval mode, no autograd) the third block -- ConvTranspose2d(256, 256) + BatchNorm + ReLU on a
+        32-wide map -- runs as the tensor-core kernel K9 and lands in the bf16 channels_last layout K3 reads (SURVEY section 8 row N1);
+        everything else, and every other case, is the stock module stack."""
+        dl = self.deconv_layers
+        if (not self.training and not torch.is_grad_enabled() and x.is_cuda and len(dl) == 9 and dl[6].out_channels == 256
+                and dl[6].in_channels % 64 == 0 and x.shape[3] * 4 == 32 and (x.shape[2] * 4) % 8 == 0):
+            y = dl[:6](x)
+            bn = dl[7]
+            return deconv_bn_relu(y, dl[6].weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        return dl(x)
 
     def init_weights(self):                            # model.py:46-56
         for m in self.modules():
@@ -81,7 +93,7 @@ class ResPoseNet(nn.Module):
 
     def _coords(self, input_img):
         if self.fused_head and not torch.is_grad_enabled():
-            feat = self.head.deconv_layers(self.backbone(input_img))
+            feat = self.head.features(self.backbone(input_img))
             fl = self.head.final_layer
             return fused_head_soft_argmax(feat, fl.weight, fl.bias, self.joint_num), feat.shape[3]
         heatmap = self.forward(input_img)
