@@ -592,7 +592,9 @@ int ihpr_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin
     rc = check_device(x_nhwc, &num_sms);
     if (rc) return rc;
     int launches = 0;
-    const char* err = ihpr::launch_deconv_bn_relu(x_nhwc, prepared, B, Cin, Cout, Hin, Win, y_nhwc, num_sms, &launches, static_cast<cudaStream_t>(stream));
+    // variants 21 / 22 / 24: clusters of 1 / 2 / 4 CTAs sharing the weight stream by TMA multicast (0: the default, see launch_deconv_bn_relu)
+    const int cluster = g_variant == 21 ? 1 : g_variant == 22 ? 2 : g_variant == 24 ? 4 : 0;
+    const char* err = ihpr::launch_deconv_bn_relu(x_nhwc, prepared, B, Cin, Cout, Hin, Win, y_nhwc, num_sms, cluster, &launches, static_cast<cudaStream_t>(stream));
     if (err) return fail(IHPR_ECUDA, "%s", err);
     g_launches = launches;
     IHPR_CUDA(cudaGetLastError());

@@ -12,8 +12,15 @@
 // columns, so every 32 KiB weight k-block feeds 8 MMAs (the weights are the operand every item re-reads: 512 KiB per accumulator pair).
 // Per k-step (one tap, 64 input channels): A0, A1 = 2 x [128 px x 64] (16 KiB each), B = [256 co x 64] (32 KiB); 16 k-steps per item,
 // 3-stage ring.  Epilogue (16 warps): y = max(0, acc * scale[co] + shift[co]) in fp32 (BatchNorm folded to scale / shift by the prep
-// kernel), bf16, staged 128 px x 64 co at a time in two alternating 16 KiB blocks and stored by 5-D TMA into the strided phase
-// positions of the NHWC output (the store of round r is only waited for in round r + 2).
+// kernel), bf16; every warp stages its own 32 pixels x 32 channels and stores them by 5-D TMA into the strided phase positions of the
+// NHWC output.
+// Clusters (CS = 2 or 4 CTAs, opt-in): half of the operand stream (64 KiB per k-step) is the weight k-block every CTA of the same
+// phase reads.  The CTAs of a cluster take the same phase and adjacent 8-row groups of one sample, each loads 1 / CS of every weight
+// k-block and TMA-multicasts it into all CS shared memories; a stage is refilled only when the MMA issuers of ALL CS CTAs have released
+// it (tcgen05.commit multicast onto every CTA's `empty` barrier).  Parity-green; on B200 the kernel turned out NOT to be bound by that
+// stream (knock-out without any loads: -4 %), so clusters of 2 only tie and clusters of 4 lose to cluster scheduling -- the default is
+// CS = 1.  What bounds it: the epilogue cannot overlap the main loop (both accumulators fill tensor memory) and costs ~5.5 k clk per
+// item next to 16.4 k clk of MMAs (profiles/r02_k9_deconv_bench.txt).
 // The last, partial wave of work items is cut into HALF items (one accumulator, 4 input rows) when that shortens the schedule: 512 items
 // on 148 SMs are 3 waves of full items + one wave of 136 halves instead of 4 waves; a batch of 4 is one wave of 128 halves.
 #include "head_tc.cuh"
@@ -33,7 +40,7 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;    // 32 KiB
 constexpr int STAGE_BYTES = NACC * A_BYTES + B_BYTES;   // 64 KiB
-constexpr int STG_BLK_BYTES = BM * 128; // 16 KiB: 128 pixels x 64 output channels of bf16
+constexpr int STG_BLK_BYTES = BM * 128; // 2 x 16 KiB of staging = 16 warps x 2 KiB
 constexpr int EPI_WARPS = 16;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * STG_BLK_BYTES + 256;
@@ -41,16 +48,29 @@ constexpr uint32_t kIdesc = make_idesc(BM, BN);
 
 struct Params {
     int B, Hin, KB;             // KB = C_in / 64
-    int items;                  // B * 4 phases * (Hin / 8)
-    int full_items;             // work units [0, full_items) are whole items; unit full_items + h is half (h & 1) of item full_items + h / 2
+    int items;                  // cluster items: B * 4 phases * (Hin / 8) / CS
+    int full_items;             // cluster work units [0, full_items) are whole items; unit full_items + h is half (h & 1) of item full_items + h / 2
     int units;                  // full_items + 2 * (items - full_items)
     const float* scale;         // (256): gamma / sqrt(var + eps)
     const float* shift;         // (256): beta - mean * scale
+    int dbg;                    // -DIHPR_TIMING_EXPERIMENTS builds only (IHPR_K9_DEBUG): 1 = no epilogue work, 2 = no operand loads, 4 = no MMAs, 8 = no output stores -- WRONG results
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+// the box lands at the same offset of EVERY CTA in `mask`, and each of them gets the complete_tx on its own barrier at `bar`'s offset
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// arrive on the barrier at `bar`'s offset in every CTA of `mask` when all MMAs this thread has issued are complete
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
@@ -63,35 +83,39 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 struct Item {
     int b, py, px, y0, nacc;
 };
-__device__ __forceinline__ Item decode(int unit, int full_items, int ygroups) {
+// `unit` counts CLUSTER work units: one unit = CS items (same sample and phase, 8-row groups CS * g + rank); units [0, full) are whole
+// items, unit full + h is half (h & 1) of cluster item full + h / 2
+__device__ __forceinline__ Item decode(int unit, int full, int ygroups, int cs, int rank) {
     Item it;
     int item = unit, half = 0;
     it.nacc = NACC;
-    if (unit >= full_items) {
-        const int h = unit - full_items;
-        item = full_items + (h >> 1);
+    if (unit >= full) {
+        const int h = unit - full;
+        item = full + (h >> 1);
         half = h & 1;
         it.nacc = 1;
     }
     const int ph = item & 3;
     const int r = item >> 2;
+    const int ygc = ygroups / cs;               // cluster 8-row groups per sample
     it.py = ph >> 1;
     it.px = ph & 1;
-    it.b = r / ygroups;
-    it.y0 = (r - it.b * ygroups) * (NACC * ROWS) + half * ROWS;
+    it.b = r / ygc;
+    it.y0 = ((r - it.b * ygc) * cs + rank) * (NACC * ROWS) + half * ROWS;
     return it;
 }
 
 //   map_x: input, 4-D {C_in, 32, Hin, B} bf16 NHWC, box {64, 32, 4, 1}, zero fill out of bounds
-//   map_w: re-laid weights, 2-D {C_in, 16 * 256}: row (phase * 4 + tap) * 256 + co, box {64, 256}
-//   map_y: output, 5-D {256, 2 (px), 32 (x0), 2 (py), Hin * B (y0 of every sample)} bf16 NHWC, box {64, 1, 32, 1, 4}
+//   map_w: re-laid weights, 2-D {C_in, 16 * 256}: row (phase * 4 + tap) * 256 + co, box {64, 256 / CS}
+//   map_y: output, 5-D {256, 2 (px), 32 (x0), 2 (py), Hin * B (y0 of every sample)} bf16 NHWC, box {32, 1, 32, 1, 1}, SWIZZLE_64B
+template <int CS>
 __global__ void __launch_bounds__(32 * (4 + EPI_WARPS), 1)
 deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
                       const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sRing = smem;                                  // [STAGES][A0 | A1 | B]
-    uint8_t* sS = sRing + STAGES * STAGE_BYTES;             // [2][128 px x 64 co] bf16 staging for the output store
+    uint8_t* sS = sRing + STAGES * STAGE_BYTES;             // [16 warps][32 px x 32 co] bf16 staging for the output stores
     uint64_t* bars = reinterpret_cast<uint64_t*>(sS + 2 * STG_BLK_BYTES);
     uint64_t* full = bars;                      // [STAGES] TMA -> MMA
     uint64_t* empty = full + STAGES;            // [STAGES] MMA -> TMA
@@ -102,9 +126,12 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ygroups = p.Hin / (NACC * ROWS);
     const int ksteps = 4 * p.KB;
+    const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster = (int)blockIdx.x / CS, nclusters = (int)gridDim.x / CS;
+    constexpr uint16_t kAll = (uint16_t)((1u << CS) - 1);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CS); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, EPI_WARPS);
         mbar_fence_init();
@@ -115,6 +142,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();     // every CTA's barriers exist before a peer multicasts into this CTA or signals it
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -122,8 +150,8 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-                const Item w = decode(unit, p.full_items, ygroups);
+            for (int unit = cluster; unit < p.units; unit += nclusters) {
+                const Item w = decode(unit, p.full_items, ygroups, CS, rank);
                 for (int tap = 0; tap < 4; ++tap) {
                     const int ty = tap >> 1, tx = tap & 1;
                     const int dy = w.py ? 1 - ty : -ty;         // py = 0: 0, -1;  py = 1: +1, 0
@@ -132,11 +160,16 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                     for (int kb = 0; kb < p.KB; ++kb, ++it) {
                         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(empty + s, ph ^ 1);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                        if (CS == 1 && (p.dbg & 2)) { mbar_arrive(full + s); continue; }
+#endif
                         mbar_expect_tx(full + s, (uint32_t)(w.nacc * A_BYTES + B_BYTES));
                         uint8_t* st = sRing + s * STAGE_BYTES;
                         tma_load_4d(st, &map_x, kb * BK, dx, w.y0 + dy, w.b, full + s);
                         if (w.nacc == NACC) tma_load_4d(st + A_BYTES, &map_x, kb * BK, dx, w.y0 + ROWS + dy, w.b, full + s);
-                        tma_load_2d(st + NACC * A_BYTES, &map_w, kb * BK, wrow, full + s);
+                        // this CTA's 1 / CS of the weight k-block goes to every CTA of the cluster (their stage s is free: `empty` counts all CS issuers)
+                        if (CS > 1) tma_load_2d_mc(st + NACC * A_BYTES + rank * (B_BYTES / CS), &map_w, kb * BK, wrow + rank * (BN / CS), full + s, kAll);
+                        else tma_load_2d(st + NACC * A_BYTES, &map_w, kb * BK, wrow, full + s);
                     }
                 }
             }
@@ -145,7 +178,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t it = 0, n = 0;
-            for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++n) {
+            for (int unit = cluster; unit < p.units; unit += nclusters, ++n) {
                 const bool both = unit < p.full_items;
                 mbar_wait(acc_empty, (n & 1) ^ 1);          // the epilogue has pulled the previous item out of tensor memory
                 tc_fence_after();
@@ -155,79 +188,91 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                     tc_fence_after();
                     const uint32_t st = smem_u32(sRing + s * STAGE_BYTES);
                     const uint64_t a0 = umma_desc(st), a1 = umma_desc(st + A_BYTES), bd = umma_desc(st + NACC * A_BYTES);
+#ifdef IHPR_TIMING_EXPERIMENTS
+                    if (!(p.dbg & 4))
+#endif
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
                         umma(tmem_base, a0 + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((ks | k16) != 0));
                         if (both) umma(tmem_base + BN, a1 + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((ks | k16) != 0));
                     }
-                    tc_commit(empty + s);
+                    if (CS > 1) tc_commit_mc(empty + s, kAll);
+                    else tc_commit(empty + s);
                 }
                 tc_commit(acc_full);
             }
         }
     } else if (warp >= 4) {
         // ================= epilogue: BatchNorm scale / shift, ReLU, bf16, TMA store into the phase positions =================
+        // Every warp works alone: its TMEM lane quarter is ONE input row (32 pixels) of the accumulator, its column group 64 output
+        // channels; it stages 32 pixels x 32 channels (2 KiB of its own) and stores them with its own TMA box -- no CTA-wide barrier
+        // anywhere in the epilogue (a first version with 512-thread named barriers around a shared staging block spent 1650 clk per
+        // 64-channel round, 13 k clk per item against 16 k clk of MMA work: profiles/r02_k9_deconv_bench.txt).
         const int e = warp - 4;
-        const int qd = warp & 3;                    // TMEM lane quarter
-        const int cg = e >> 2;                      // 16 of the 64 output channels of a round
-        const int row = qd * 32 + lane;             // pixel of the accumulator = TMEM lane = staging row
+        const int qd = warp & 3;                    // TMEM lane quarter (hardware: warp id % 4) = input row within the accumulator
+        const int cg = e >> 2;                      // 64 of the 256 output channels
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const int sw = row & 7;
-        const bool elected = e == 0 && lane == 0;
-        uint32_t n = 0, rr = 0;                     // rr: running round count = which staging block
-        for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++n) {
-            const Item w = decode(unit, p.full_items, ygroups);
-            const int rounds = 4 * w.nacc;          // round = (accumulator, 64 output channels)
+        uint8_t* stg = sS + e * 2048;               // [32 pixels][64 bytes], SWIZZLE_64B: 16-byte chunk ^= (pixel >> 1) & 3
+        const int swz = (lane >> 1) & 3;
+        uint32_t n = 0;
+        for (int unit = cluster; unit < p.units; unit += nclusters, ++n) {
+            const Item w = decode(unit, p.full_items, ygroups, CS, rank);
+            const int rounds = 2 * w.nacc;          // round = (accumulator, 32 of this warp's 64 output channels)
             mbar_wait(acc_full, n & 1);
             tc_fence_after();
+#ifdef IHPR_TIMING_EXPERIMENTS
+            if (p.dbg & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                continue;
+            }
+#endif
+            // (Pulling the whole item out of tensor memory first -- 64 packed registers per thread -- so that the stores run underneath
+            // the next item's main loop was tried: at 96 registers per thread it spills ~1 KiB per thread.)
 #pragma unroll 1
-            for (int r = 0; r < rounds; ++r, ++rr) {
-                const int a = r >> 2;
-                const int co0 = (r & 3) * 64 + cg * 16;
-                uint32_t v[16];
-                tmem_ld16_issue(tmem_base + lane_off + (uint32_t)(a * BN + co0), v);
-                float4 sc[4], sh[4];
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    sc[i4] = __ldg(reinterpret_cast<const float4*>(p.scale + co0) + i4);
-                    sh[i4] = __ldg(reinterpret_cast<const float4*>(p.shift + co0) + i4);
-                }
-                tmem_ld16_wait(v);
+            for (int r = 0; r < rounds; ++r) {
+                const int a = r >> 1;
+                const int co0 = cg * 64 + (r & 1) * 32;
+                float v[32];
+                tmem_ld32(tmem_base + lane_off + (uint32_t)(a * BN + co0), v);
                 if (r == rounds - 1) {                      // the accumulators are in registers / stored: the next item's MMAs may start
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty);
                 }
-                uint32_t o[8];
+                uint32_t o[16];
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float y0 = fmaxf(fmaf(__uint_as_float(v[4 * i4]), sc[i4].x, sh[i4].x), 0.f);
-                    const float y1 = fmaxf(fmaf(__uint_as_float(v[4 * i4 + 1]), sc[i4].y, sh[i4].y), 0.f);
-                    const float y2 = fmaxf(fmaf(__uint_as_float(v[4 * i4 + 2]), sc[i4].z, sh[i4].z), 0.f);
-                    const float y3 = fmaxf(fmaf(__uint_as_float(v[4 * i4 + 3]), sc[i4].w, sh[i4].w), 0.f);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co0) + i4);
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co0) + i4);
+                    const float y0 = fmaxf(fmaf(v[4 * i4], sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f);
+                    const float y2 = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f), y3 = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f);
                     o[2 * i4] = Elem<__nv_bfloat16>::pk(y0, y1);
                     o[2 * i4 + 1] = Elem<__nv_bfloat16>::pk(y2, y3);
                 }
-                // staging block rr & 1 was last read by the store of round rr - 2: at most the store of round rr - 1 may still be in flight
-                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                named_bar_sync(1, EPI_WARPS * 32);
-                uint8_t* blk = sS + (rr & 1) * STG_BLK_BYTES;
-                uint8_t* srow = blk + row * 128;
-                sts16(srow + (((2 * cg) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
-                sts16(srow + (((2 * cg + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                if (lane == 0) tma_store_wait_read();       // this warp's previous store has read the staging piece
+                __syncwarp();
+                uint8_t* srow = stg + lane * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sts16(srow + ((j ^ swz) << 4), make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
                 fence_async_smem();
-                named_bar_sync(2, EPI_WARPS * 32);
-                if (elected) {
-                    tma_store_5d(&map_y, blk, (r & 3) * 64, w.px, 0, w.py, w.b * p.Hin + w.y0 + a * ROWS);
+                __syncwarp();
+#ifdef IHPR_TIMING_EXPERIMENTS
+                if (p.dbg & 8) continue;
+#endif
+                if (lane == 0) {
+                    tma_store_5d(&map_y, stg, co0, w.px, 0, w.py, w.b * p.Hin + w.y0 + a * ROWS + qd);
                     tma_store_commit();
                 }
             }
         }
-        if (elected) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();     // no CTA leaves while a peer may still signal its barriers
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
@@ -265,12 +310,13 @@ __global__ void deconv_prep_kernel(const __nv_bfloat16* __restrict__ w, int Cin,
 // ---- host side --------------------------------------------------------------------------------------------------
 size_t deconv_workspace_bytes(int Cin, int Cout) { return (size_t)16 * Cin * Cout * 2 + 2 * (size_t)Cout * sizeof(float) + 512; }
 
-static bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+static bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     tc::EncodeTiledFn enc = tc::encode_tiled();
     if (!enc) return false;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static void carve(void* workspace, int Cin, int Cout, __nv_bfloat16** wp, float** scale, float** shift) {
@@ -291,13 +337,47 @@ void launch_deconv_prepare(const void* weight, const float* gamma, const float* 
     ++*launches;
 }
 
-const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int* launches,
-                                  cudaStream_t s) {
+template <int CS>
+static const char* launch_k9(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, k9::Params p, int T, int num_sms, cudaStream_t s) {
+    using namespace k9;
+    auto kern = deconv_bn_relu_kernel<CS>;
+    const size_t smem = SMEM_BYTES + 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return "cudaFuncSetAttribute failed (deconv_bn_relu_kernel)";
+    // whole waves of full items, then the rest as half items if that ends sooner (time in half-item waves); G = clusters that run at once
+    const int G = num_sms / CS;
+    p.items = T / CS;
+    const int whole = (p.items / G) * G, rest = p.items - whole;
+    const int t_full = 2 * ((p.items + G - 1) / G), t_half = 2 * (p.items / G) + (2 * rest + G - 1) / G;
+    p.full_items = t_half < t_full ? whole : p.items;
+    p.units = p.full_items + 2 * (p.items - p.full_items);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CS * (p.units < G ? p.units : G)));
+    cfg.blockDim = dim3(32 * (4 + EPI_WARPS));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, mx, mw, my, p) != cudaSuccess) return "deconv_bn_relu_kernel launch failed";
+    return nullptr;
+}
+
+// cluster: 0 = default (one CTA per SM, no cluster), else 1 / 2 / 4 CTAs per cluster (halved until it divides the 8-row groups of a sample)
+const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int cluster,
+                                  int* launches, cudaStream_t s) {
     using namespace k9;
     (void)Win;
     __nv_bfloat16* wp;
     float *scale, *shift;
     carve(const_cast<void*>(prepared), Cin, Cout, &wp, &scale, &shift);
+    const int ygroups = Hin / (NACC * ROWS);
+    int cs = cluster;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;      // measured on B200: clusters of 2 tie (62.0 vs 59.9 us at B = 32), clusters of 4 lose (121 us)
+    while (cs > 1 && (ygroups % cs != 0 || num_sms < cs)) cs >>= 1;
     CUtensorMap map_x, map_w, map_y;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)WIN, (cuuint64_t)Hin, (cuuint64_t)B};
@@ -305,29 +385,24 @@ const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int 
         const cuuint32_t box[4] = {BK, WIN, ROWS, 1};
         if (!encode(&map_x, x_nhwc, 4, dims, strides, box)) return "cuTensorMapEncodeTiled failed for the deconv input";
     }
-    if (!tc::make_map(&map_w, wp, (uint64_t)16 * Cout, (uint64_t)Cin, BN)) return "cuTensorMapEncodeTiled failed for the deconv weights";
+    if (!tc::make_map(&map_w, wp, (uint64_t)16 * Cout, (uint64_t)Cin, BN / cs)) return "cuTensorMapEncodeTiled failed for the deconv weights";
     {
         const cuuint64_t dims[5] = {(cuuint64_t)Cout, 2, (cuuint64_t)WIN, 2, (cuuint64_t)Hin * B};
         const cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * WIN * Cout * 2, (cuuint64_t)2 * 2 * WIN * Cout * 2};
-        const cuuint32_t box[5] = {BK, 1, WIN, 1, ROWS};
-        if (!encode(&map_y, y_nhwc, 5, dims, strides, box)) return "cuTensorMapEncodeTiled failed for the deconv output";
+        const cuuint32_t box[5] = {32, 1, WIN, 1, 1};
+        if (!encode(&map_y, y_nhwc, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return "cuTensorMapEncodeTiled failed for the deconv output";
     }
     Params p;
     p.B = B; p.Hin = Hin; p.KB = Cin / BK;
-    p.items = B * 4 * (Hin / (NACC * ROWS));
-    // whole waves of full items, then the rest as half items if that ends sooner (time in half-item waves)
-    {
-        const int G = num_sms, T = p.items;
-        const int whole = (T / G) * G, rest = T - whole;
-        const int t_full = 2 * ((T + G - 1) / G), t_half = 2 * (T / G) + (2 * rest + G - 1) / G;
-        p.full_items = t_half < t_full ? whole : T;
-        p.units = p.full_items + 2 * (T - p.full_items);
-    }
     p.scale = scale; p.shift = shift;
-    const size_t smem = SMEM_BYTES + 1024;
-    if (cudaFuncSetAttribute(deconv_bn_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return "cudaFuncSetAttribute failed (deconv_bn_relu_kernel)";
-    deconv_bn_relu_kernel<<<p.units < num_sms ? p.units : num_sms, 32 * (4 + EPI_WARPS), smem, s>>>(map_x, map_w, map_y, p);
+    p.dbg = 0;
+#ifdef IHPR_TIMING_EXPERIMENTS
+    if (const char* e = getenv("IHPR_K9_DEBUG")) p.dbg = atoi(e);
+#endif
+    const int T = B * 4 * ygroups;
+    const char* err = cs == 4 ? launch_k9<4>(map_x, map_w, map_y, p, T, num_sms, s) : cs == 2 ? launch_k9<2>(map_x, map_w, map_y, p, T, num_sms, s)
+                                                                                              : launch_k9<1>(map_x, map_w, map_y, p, T, num_sms, s);
+    if (err) return err;
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? nullptr : "deconv_bn_relu_kernel launch failed";
 }

@@ -399,7 +399,7 @@ const char* launch_head_bwd_params(const void* x_nhwc, const void* w, const floa
 size_t deconv_workspace_bytes(int Cin, int Cout);
 void launch_deconv_prepare(const void* weight, const float* gamma, const float* beta, const float* mean, const float* var, float eps, int Cin, int Cout,
                            void* workspace, int* launches, cudaStream_t s);
-const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int* launches,
-                                  cudaStream_t s);
+const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int cluster,
+                                  int* launches, cudaStream_t s);
 
 }  // namespace ihpr

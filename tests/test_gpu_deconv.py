@@ -17,6 +17,13 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _reset_variant():
+    yield
+    import ihpr_b200
+    ihpr_b200.set_variant(0)
+
+
 def _problem(B, Cin, Hin, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, Cin, Hin, 32, generator=g).to(torch.bfloat16)
@@ -40,9 +47,11 @@ def _truth64(x, w, gamma, beta, mean, var, eps, dev):
     (1, 128, 16),       # C_in = 128: two k-blocks per tap
     (37, 256, 32),      # 592 work items: persistent CTAs walk several, the ring wraps across items
 ])
-def test_deconv_bn_relu_vs_torch_fp64(case, dev):
+@pytest.mark.parametrize("variant", [0, 21, 22, 24])    # 0: default cluster size; 21 / 22 / 24: clusters of 1 / 2 / 4 CTAs (TMA multicast of the weights)
+def test_deconv_bn_relu_vs_torch_fp64(case, variant, dev):
     import ihpr_b200
     B, Cin, Hin = case
+    ihpr_b200.set_variant(variant)
     x, w, gamma, beta, mean, var = _problem(B, Cin, Hin, seed=B * 1000 + Cin + Hin)
     eps = 1e-5
     want = _truth64(x, w, gamma, beta, mean, var, eps, dev)

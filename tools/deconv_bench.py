@@ -12,8 +12,10 @@ ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--J", type=int, default=18)
 ap.add_argument("--D", type=int, default=64)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--variant", type=int, default=0, help="21 / 22 / 24: K9 on clusters of 1 / 2 / 4 CTAs")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
+ihpr_b200.set_variant(a.variant)
 torch.backends.cudnn.benchmark = True
 B, J, D = a.B, a.J, a.D
 x = torch.randn(B, 256, 32, 32, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -51,7 +53,7 @@ with torch.no_grad():
     c9 = ihpr_b200.fused_head_soft_argmax(y9, wb, bias, J)
     cs = ihpr_b200.soft_argmax(final(ys), J)
 flop = 2.0 * B * 64 * 64 * 256 * 1024
-print(json.dumps({"B": B, "k9_us": round(t_k9, 1), "k9_TFLOPs": round(flop / t_k9 / 1e6, 1), "stock_deconv_bn_relu_us": round(t_stock, 1),
+print(json.dumps({"variant": a.variant, "B": B, "k9_us": round(t_k9, 1), "k9_TFLOPs": round(flop / t_k9 / 1e6, 1), "stock_deconv_bn_relu_us": round(t_stock, 1),
                   "stock_deconv_only_us": round(t_conv, 1), "speedup": round(t_stock / t_k9, 2),
                   "max_rel_diff_vs_stock_bf16": round(((y9.float() - ys.float()).abs().max() / ys.float().abs().max()).item(), 5),
                   "tail_k9_k3_us": round(t_tail, 1), "tail_stock_conv_k1_us": round(t_tail_stock, 1), "tail_speedup": round(t_tail_stock / t_tail, 2),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K1c, K5, K5c with
-clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6) with finiteness checks: a quick all-kernel smoke on a B200, and the
+clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6, K9) with finiteness checks: a quick all-kernel smoke on a B200, and the
 driver to put under `compute-sanitizer --tool memcheck|racecheck|synccheck` where the pool allows it (round 1's pool does not)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -56,6 +56,15 @@ for v in (0, 3):
     torch.cuda.synchronize()
     assert torch.isfinite(loss).item() and torch.isfinite(x.grad.float()).all().item()
 ihpr_b200.set_variant(0)
+# K9: deconv3 + BatchNorm + ReLU (full items and half items)
+for Bq in (1, 10):
+    xq = torch.randn(Bq, 256, 32, 32, generator=g).to(torch.bfloat16).to(dev)
+    wq = (torch.randn(256, 256, 4, 4, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    with torch.no_grad():
+        yq = ihpr_b200.deconv_bn_relu(xq, wq, torch.ones(256, device=dev), torch.zeros(256, device=dev), torch.zeros(256, device=dev),
+                                      torch.ones(256, device=dev), 1e-5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(yq.float()).all().item()
 # K6: test-time post-processing
 B, J = 3, 18
 coords = torch.rand(B, J, 3, device=dev) * 64
