@@ -415,6 +415,16 @@ def run_b200(args):
         except Exception as e:      # noqa: the headline line must survive a failure of the secondary record
             train = {"error": repr(e)[:300]}
 
+    # ---- the test path (main/test.py:62-65) at test_batch_size and at the training batch, rank 0 only (it does not shard below a batch)
+    infer = None
+    if not args.no_train and args.dtype == "f32" and rank == 0:
+        try:
+            infer = infer_record(dev)
+        except Exception as e:      # noqa
+            infer = {"error": repr(e)[:300]}
+    if world > 1:
+        dist.barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -483,7 +493,7 @@ def run_b200(args):
         "notes": {"residency": "HBM for value / roofline, pinned host memory for e2e", "variant": ihpr_b200.get_variant(),
                   "api": "ihpr_b200.JointLocationLoss().forward_backward(heat, gt, vis, have_depth)  [one launch: K5]"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": extra, "cpu_baseline": cpu,
-        "train": train,
+        "train": train, "infer": infer,
     }
     print(json.dumps(line))
     if world > 1:
@@ -643,6 +653,50 @@ def train_record(args, dev, world, rank):
     except Exception as e:      # noqa: the eager record stands on its own
         rec["cuda_graph"] = {"error": repr(e)[:300]}
     return rec
+
+
+def infer_record(dev, joint_num=18, depth_dim=64):
+    """The `infer` sub-record: ResNet-50 + head -> (B, J, 3) coordinates under eval / no_grad, bf16 autocast for the stock convolutions
+    (main/test.py:53-65 with cfg.test_batch_size = 4, main/config.py:44, and at B = 32).  `value` is ResPoseNet(fused_head=True).predict:
+    deconv block 3 + BatchNorm + ReLU as K9, final_layer + soft_argmax as K3 (nothing heat-map sized stored); `stock_tail` is the same
+    network with the stock module stack producing the heat-map and K1 reading it.  CUDA events around 10 calls each."""
+    import types
+    import torch
+    import ihpr_b200
+    from ihpr_b200.model import get_pose_net
+    cfg = types.SimpleNamespace(resnet_type=50, depth_dim=depth_dim, input_shape=(256, 256), output_shape=(64, 64))
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, joint_num, fused_head=True).to(dev).to(memory_format=torch.channels_last).eval()
+    out = {"metric": "inference samples/s", "unit": "samples/s", "data": "synthetic", "dtype": "bf16",
+           "config": {"workload": "ResNet-50 + deconv head -> soft-argmax coordinates (eval, no_grad, bf16 autocast), synthetic 256x256, J=%d, D=%d"
+                                  % (joint_num, depth_dim)}}
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            fn()
+        t1.record()
+        torch.cuda.synchronize(dev)
+        return t0.elapsed_time(t1) / iters
+
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for B in (4, 32):
+            img = torch.randn(B, 3, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+            net.fused_head = True
+            ms = timed(lambda: net.predict(img))
+            c_fused = net.predict(img)
+            net.fused_head = False
+            ms_stock = timed(lambda: net.predict(img))
+            c_stock = net.predict(img)
+            out["B%d" % B] = {"value": B / ms * 1e3, "ms_per_batch": ms, "stock_tail": {"value": B / ms_stock * 1e3, "ms_per_batch": ms_stock},
+                              "max_coord_diff_vs_stock_tail": float((c_fused - c_stock).abs().max().item())}
+    del net
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_train(args):
