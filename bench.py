@@ -663,7 +663,7 @@ def infer_record(dev, joint_num=18, depth_dim=64):
     import types
     import torch
     import ihpr_b200
-    from ihpr_b200.model import get_pose_net
+    from ihpr_b200.model import GraphedPredict, get_pose_net
     cfg = types.SimpleNamespace(resnet_type=50, depth_dim=depth_dim, input_shape=(256, 256), output_shape=(64, 64))
     torch.manual_seed(0)
     net = get_pose_net(cfg, True, joint_num, fused_head=True).to(dev).to(memory_format=torch.channels_last).eval()
@@ -694,6 +694,15 @@ def infer_record(dev, joint_num=18, depth_dim=64):
             c_stock = net.predict(img)
             out["B%d" % B] = {"value": B / ms * 1e3, "ms_per_batch": ms, "stock_tail": {"value": B / ms_stock * 1e3, "ms_per_batch": ms_stock},
                               "max_coord_diff_vs_stock_tail": float((c_fused - c_stock).abs().max().item())}
+            try:        # the same call replayed as ONE CUDA graph (ihpr_b200.model.GraphedPredict): what takes the host out of the test loop
+                net.fused_head = True
+                gp = GraphedPredict(net, img, autocast_dtype=torch.bfloat16)
+                ms_g = timed(lambda: gp(img))
+                out["B%d" % B]["cuda_graph"] = {"value": B / ms_g * 1e3, "ms_per_batch": ms_g,
+                                                "max_coord_diff_vs_eager": float((gp(img) - c_fused).abs().max().item())}
+                del gp
+            except Exception as e:      # noqa
+                out["B%d" % B]["cuda_graph"] = {"error": repr(e)[:200]}
     del net
     torch.cuda.empty_cache()
     return out

@@ -153,3 +153,28 @@ def test_inference_head_runs_k9_then_k3_and_matches_the_stock_head(dev):
     # training mode / autograd keep the stock stack (batch statistics)
     net.train()
     assert net.head.features(net.backbone(x)).dtype == torch.float32
+
+
+def test_graphed_predict_replays_the_test_path(dev):
+    """GraphedPredict: backbone + head + K9 + K3 (+ the flip pass and K6) captured once, replayed for new batches; same numbers as the
+    eager predict() on each batch."""
+    from ihpr_b200.model import GraphedPredict, get_pose_net
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=32, input_shape=(256, 256), output_shape=(64, 64))
+    torch.manual_seed(3)
+    J = 4
+    net = get_pose_net(cfg, True, J, fused_head=True).to(dev)
+    torch.nn.init.normal_(net.head.final_layer.weight, std=0.02)
+    with pytest.raises(ValueError):
+        GraphedPredict(net, torch.randn(4, 3, 256, 256, device=dev))      # still in training mode
+    net.eval()
+    pairs = ((0, 1), (2, 3))
+    gp = GraphedPredict(net, torch.randn(4, 3, 256, 256, device=dev), flip_pairs=pairs)
+    for seed in (10, 11, 12):
+        img = torch.randn(4, 3, 256, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+        got = gp(img).clone()
+        with torch.no_grad():
+            want = net.predict(img, flip_pairs=pairs)
+        assert got.shape == (4, J, 3)
+        assert (got - want).abs().max().item() <= 1e-3, (got - want).abs().max().item()
+    with pytest.raises(ValueError):
+        gp(torch.randn(2, 3, 256, 256, device=dev))
