@@ -120,8 +120,8 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     uint64_t* full = bars;                      // [STAGES] TMA -> MMA
     uint64_t* empty = full + STAGES;            // [STAGES] MMA -> TMA
     uint64_t* acc_full = empty + STAGES;        // [1] MMA -> epilogue
-    uint64_t* acc_empty = acc_full + 1;         // [1] epilogue -> MMA (EPI_WARPS arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_empty = acc_full + 1;         // [2] epilogue -> MMA, one per accumulator (EPI_WARPS arrivals): accumulator 0 is drained first
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ygroups = p.Hin / (NACC * ROWS);
@@ -133,7 +133,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CS); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, EPI_WARPS);
+        for (int a = 0; a < NACC; ++a) mbar_init(acc_empty + a, EPI_WARPS);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -177,27 +177,49 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t it = 0, n = 0;
-            for (int unit = cluster; unit < p.units; unit += nclusters, ++n) {
-                const bool both = unit < p.full_items;
-                mbar_wait(acc_empty, (n & 1) ^ 1);          // the epilogue has pulled the previous item out of tensor memory
-                tc_fence_after();
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(full + s, ph);
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(sRing + s * STAGE_BYTES);
-                    const uint64_t a0 = umma_desc(st), a1 = umma_desc(st + A_BYTES), bd = umma_desc(st + NACC * A_BYTES);
+            // The epilogue of the previous item drains accumulator 0 first and hands it back ~2.7 k clk before accumulator 1, so an item
+            // STARTS SKEWED: the accumulator-0 MMAs of the first STAGES k-steps are issued as soon as accumulator 0 is free (their stages are
+            // already loaded), the accumulator-1 MMAs of those k-steps follow when accumulator 1 is, then both run interleaved per k-step.
+            uint32_t it = 0;
+            uint32_t n_acc[NACC] = {0, 0};             // items that have used each accumulator (phase of its acc_empty barrier)
+            auto mma_ks = [&](uint32_t i, int ks, int acc) {       // the four MMAs of k-step ks (ring position i) into one accumulator
+                const uint32_t st = smem_u32(sRing + (i % STAGES) * STAGE_BYTES);
+                const uint64_t ad = umma_desc(st + acc * A_BYTES), bd = umma_desc(st + NACC * A_BYTES);
 #ifdef IHPR_TIMING_EXPERIMENTS
-                    if (!(p.dbg & 4))
+                if (p.dbg & 4) return;
 #endif
 #pragma unroll
-                    for (int k16 = 0; k16 < BK / 16; ++k16) {
-                        umma(tmem_base, a0 + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((ks | k16) != 0));
-                        if (both) umma(tmem_base + BN, a1 + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((ks | k16) != 0));
-                    }
-                    if (CS > 1) tc_commit_mc(empty + s, kAll);
-                    else tc_commit(empty + s);
+                for (int k16 = 0; k16 < BK / 16; ++k16) umma(tmem_base + acc * BN, ad + 2 * k16, bd + 2 * k16, kIdesc, (uint32_t)((ks | k16) != 0));
+            };
+            auto release = [&](uint32_t i) {
+                if (CS > 1) tc_commit_mc(empty + i % STAGES, kAll);
+                else tc_commit(empty + i % STAGES);
+            };
+            for (int unit = cluster; unit < p.units; unit += nclusters) {
+                const bool both = unit < p.full_items;
+                const int skew = both ? (ksteps < STAGES ? ksteps : STAGES) : 0;
+                mbar_wait(acc_empty, (n_acc[0]++ & 1) ^ 1);         // the epilogue has pulled the previous item out of accumulator 0
+                tc_fence_after();
+                for (int ks = 0; ks < skew; ++ks) {
+                    mbar_wait(full + (it + ks) % STAGES, ((it + ks) / STAGES) & 1);
+                    tc_fence_after();
+                    mma_ks(it + ks, ks, 0);
+                }
+                if (both) {
+                    mbar_wait(acc_empty + 1, (n_acc[1]++ & 1) ^ 1);
+                    tc_fence_after();
+                }
+                for (int ks = 0; ks < skew; ++ks) {
+                    mma_ks(it + ks, ks, 1);
+                    release(it + ks);
+                }
+                it += skew;
+                for (int ks = skew; ks < ksteps; ++ks, ++it) {
+                    mbar_wait(full + it % STAGES, (it / STAGES) & 1);
+                    tc_fence_after();
+                    mma_ks(it, ks, 0);
+                    if (both) mma_ks(it, ks, 1);
+                    release(it);
                 }
                 tc_commit(acc_full);
             }
@@ -224,7 +246,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             if (p.dbg & 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
+                if (lane == 0) { mbar_arrive(acc_empty); if (w.nacc == NACC) mbar_arrive(acc_empty + 1); }
                 continue;
             }
 #endif
@@ -236,10 +258,10 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 const int co0 = cg * 64 + (r & 1) * 32;
                 float v[32];
                 tmem_ld32(tmem_base + lane_off + (uint32_t)(a * BN + co0), v);
-                if (r == rounds - 1) {                      // the accumulators are in registers / stored: the next item's MMAs may start
+                if (r & 1) {                                // this accumulator is in registers / stored: the next item's MMAs into it may start
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (lane == 0) mbar_arrive(acc_empty + a);
                 }
                 uint32_t o[16];
 #pragma unroll
