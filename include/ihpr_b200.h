@@ -211,7 +211,8 @@ int ihpr_head_integral_l1_bwd_params(const void *x_nhwc, const void *weight, con
  *   ihpr_deconv_bn_relu -- per batch (1 launch): x_nhwc (B, Hin, Win, C_in) bf16 (the channels_last layout of (B, C_in, Hin, Win))
  *     -> y_nhwc (B, 2 Hin, 2 Win, C_out) bf16, exactly the operand ihpr_head_softargmax_fwd reads; `prepared` is a workspace
  *     ihpr_deconv_bn_relu_prepare filled on the same stream (or earlier).
- * Needs C_out == 256, C_in % 64 == 0, Win == 32, Hin % 8 == 0.  Inference only (running statistics; no backward). */
+ * Needs C_out == 256, C_in % 64 == 0 and Win == 32 with Hin % 8 == 0 or Win == 16 with Hin % 16 == 0 -- the second and the third
+ * block of the reference head (16 x 16 -> 32 x 32 -> 64 x 64) for its 256 x 256 input.  Inference only (running statistics; no backward). */
 size_t ihpr_deconv_bn_relu_workspace_bytes(int Cin, int Cout);
 int ihpr_deconv_bn_relu_prepare(const void *weight, const float *gamma, const float *beta,
                                 const float *running_mean, const float *running_var, float eps,

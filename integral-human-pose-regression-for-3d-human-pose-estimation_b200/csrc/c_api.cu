@@ -584,7 +584,8 @@ int ihpr_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin
     if (B <= 0) return fail(IHPR_EINVAL, "non-positive batch");
     int rc = deconv_channel_check(Cin, Cout);
     if (rc) return rc;
-    if (Win != 32 || Hin <= 0 || Hin % 8 != 0) return fail(IHPR_EINVAL, "deconv_bn_relu needs an input of width 32 and a height that is a multiple of 8 (got %dx%d)", Hin, Win);
+    if ((Win != 32 && Win != 16) || Hin <= 0 || Hin % (256 / Win) != 0)
+        return fail(IHPR_EINVAL, "deconv_bn_relu needs an input of width 32 (height %% 8 == 0) or 16 (height %% 16 == 0), got %dx%d", Hin, Win);
     if ((long long)B * Hin > 0x7fffffffLL / 4) return fail(IHPR_EINVAL, "B*H does not fit");
     if (((uintptr_t)x_nhwc | (uintptr_t)y_nhwc) & 15) return fail(IHPR_EINVAL, "x / y must be 16-byte aligned");
     if ((uintptr_t)prepared & 255) return fail(IHPR_EINVAL, "the prepared workspace must be 256-byte aligned");

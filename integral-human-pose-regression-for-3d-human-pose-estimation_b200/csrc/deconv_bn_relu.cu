@@ -33,8 +33,7 @@ using namespace tc;
 constexpr int BM = 128;                 // pixels per accumulator: 4 input rows x 32 columns
 constexpr int BN = 256;                 // output channels (one UMMA N)
 constexpr int BK = 64;
-constexpr int WIN = 32;                 // input width (= the x extent of the TMA box)
-constexpr int ROWS = 4;                 // input rows per accumulator
+// input width Win = 32 or 16 (the x extent of the TMA boxes); an accumulator is rows = 128 / Win input rows (4 or 8)
 constexpr int NACC = 2;
 constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KiB
@@ -48,6 +47,8 @@ constexpr uint32_t kIdesc = make_idesc(BM, BN);
 
 struct Params {
     int B, Hin, KB;             // KB = C_in / 64
+    int rows;                   // input rows per accumulator: 128 / Win
+    int wrows;                  // input rows per epilogue warp (32 pixels): 32 / Win
     int items;                  // cluster items: B * 4 phases * (Hin / 8) / CS
     int full_items;             // cluster work units [0, full_items) are whole items; unit full_items + h is half (h & 1) of item full_items + h / 2
     int units;                  // full_items + 2 * (items - full_items)
@@ -85,7 +86,7 @@ struct Item {
 };
 // `unit` counts CLUSTER work units: one unit = CS items (same sample and phase, 8-row groups CS * g + rank); units [0, full) are whole
 // items, unit full + h is half (h & 1) of cluster item full + h / 2
-__device__ __forceinline__ Item decode(int unit, int full, int ygroups, int cs, int rank) {
+__device__ __forceinline__ Item decode(int unit, int full, int ygroups, int cs, int rank, int rows) {
     Item it;
     int item = unit, half = 0;
     it.nacc = NACC;
@@ -101,13 +102,13 @@ __device__ __forceinline__ Item decode(int unit, int full, int ygroups, int cs, 
     it.py = ph >> 1;
     it.px = ph & 1;
     it.b = r / ygc;
-    it.y0 = ((r - it.b * ygc) * cs + rank) * (NACC * ROWS) + half * ROWS;
+    it.y0 = ((r - it.b * ygc) * cs + rank) * (NACC * rows) + half * rows;
     return it;
 }
 
-//   map_x: input, 4-D {C_in, 32, Hin, B} bf16 NHWC, box {64, 32, 4, 1}, zero fill out of bounds
+//   map_x: input, 4-D {C_in, Win, Hin, B} bf16 NHWC, box {64, Win, 128 / Win, 1}, zero fill out of bounds
 //   map_w: re-laid weights, 2-D {C_in, 16 * 256}: row (phase * 4 + tap) * 256 + co, box {64, 256 / CS}
-//   map_y: output, 5-D {256, 2 (px), 32 (x0), 2 (py), Hin * B (y0 of every sample)} bf16 NHWC, box {32, 1, 32, 1, 1}, SWIZZLE_64B
+//   map_y: output, 5-D {256, 2 (px), Win (x0), 2 (py), Hin * B (y0 of every sample)} bf16 NHWC, box {32, 1, Win, 1, 32 / Win}, SWIZZLE_64B
 template <int CS>
 __global__ void __launch_bounds__(32 * (4 + EPI_WARPS), 1)
 deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
@@ -124,7 +125,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ygroups = p.Hin / (NACC * ROWS);
+    const int ygroups = p.Hin / (NACC * p.rows);
     const int ksteps = 4 * p.KB;
     const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
     const int cluster = (int)blockIdx.x / CS, nclusters = (int)gridDim.x / CS;
@@ -151,7 +152,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         if (lane == 0) {
             uint32_t it = 0;
             for (int unit = cluster; unit < p.units; unit += nclusters) {
-                const Item w = decode(unit, p.full_items, ygroups, CS, rank);
+                const Item w = decode(unit, p.full_items, ygroups, CS, rank, p.rows);
                 for (int tap = 0; tap < 4; ++tap) {
                     const int ty = tap >> 1, tx = tap & 1;
                     const int dy = w.py ? 1 - ty : -ty;         // py = 0: 0, -1;  py = 1: +1, 0
@@ -166,7 +167,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                         mbar_expect_tx(full + s, (uint32_t)(w.nacc * A_BYTES + B_BYTES));
                         uint8_t* st = sRing + s * STAGE_BYTES;
                         tma_load_4d(st, &map_x, kb * BK, dx, w.y0 + dy, w.b, full + s);
-                        if (w.nacc == NACC) tma_load_4d(st + A_BYTES, &map_x, kb * BK, dx, w.y0 + ROWS + dy, w.b, full + s);
+                        if (w.nacc == NACC) tma_load_4d(st + A_BYTES, &map_x, kb * BK, dx, w.y0 + p.rows + dy, w.b, full + s);
                         // this CTA's 1 / CS of the weight k-block goes to every CTA of the cluster (their stage s is free: `empty` counts all CS issuers)
                         if (CS > 1) tma_load_2d_mc(st + NACC * A_BYTES + rank * (B_BYTES / CS), &map_w, kb * BK, wrow + rank * (BN / CS), full + s, kAll);
                         else tma_load_2d(st + NACC * A_BYTES, &map_w, kb * BK, wrow, full + s);
@@ -238,7 +239,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int swz = (lane >> 1) & 3;
         uint32_t n = 0;
         for (int unit = cluster; unit < p.units; unit += nclusters, ++n) {
-            const Item w = decode(unit, p.full_items, ygroups, CS, rank);
+            const Item w = decode(unit, p.full_items, ygroups, CS, rank, p.rows);
             const int rounds = 2 * w.nacc;          // round = (accumulator, 32 of this warp's 64 output channels)
             mbar_wait(acc_full, n & 1);
             tc_fence_after();
@@ -284,7 +285,7 @@ deconv_bn_relu_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 if (p.dbg & 8) continue;
 #endif
                 if (lane == 0) {
-                    tma_store_5d(&map_y, stg, co0, w.px, 0, w.py, w.b * p.Hin + w.y0 + a * ROWS + qd);
+                    tma_store_5d(&map_y, stg, co0, w.px, 0, w.py, w.b * p.Hin + w.y0 + a * p.rows + qd * p.wrows);
                     tma_store_commit();
                 }
             }
@@ -392,30 +393,30 @@ static const char* launch_k9(const CUtensorMap& mx, const CUtensorMap& mw, const
 const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int cluster,
                                   int* launches, cudaStream_t s) {
     using namespace k9;
-    (void)Win;
     __nv_bfloat16* wp;
     float *scale, *shift;
     carve(const_cast<void*>(prepared), Cin, Cout, &wp, &scale, &shift);
-    const int ygroups = Hin / (NACC * ROWS);
+    const int rows = BM / Win, ygroups = Hin / (NACC * rows);
     int cs = cluster;
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;      // measured on B200: clusters of 2 tie (62.0 vs 59.9 us at B = 32), clusters of 4 lose (121 us)
     while (cs > 1 && (ygroups % cs != 0 || num_sms < cs)) cs >>= 1;
     CUtensorMap map_x, map_w, map_y;
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)WIN, (cuuint64_t)Hin, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)WIN * Cin * 2, (cuuint64_t)Hin * WIN * Cin * 2};
-        const cuuint32_t box[4] = {BK, WIN, ROWS, 1};
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2};
+        const cuuint32_t box[4] = {BK, (cuuint32_t)Win, (cuuint32_t)rows, 1};
         if (!encode(&map_x, x_nhwc, 4, dims, strides, box)) return "cuTensorMapEncodeTiled failed for the deconv input";
     }
     if (!tc::make_map(&map_w, wp, (uint64_t)16 * Cout, (uint64_t)Cin, BN / cs)) return "cuTensorMapEncodeTiled failed for the deconv weights";
     {
-        const cuuint64_t dims[5] = {(cuuint64_t)Cout, 2, (cuuint64_t)WIN, 2, (cuuint64_t)Hin * B};
-        const cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * WIN * Cout * 2, (cuuint64_t)2 * 2 * WIN * Cout * 2};
-        const cuuint32_t box[5] = {32, 1, WIN, 1, 1};
+        const cuuint64_t dims[5] = {(cuuint64_t)Cout, 2, (cuuint64_t)Win, 2, (cuuint64_t)Hin * B};
+        const cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)2 * Cout * 2, (cuuint64_t)2 * Win * Cout * 2, (cuuint64_t)2 * 2 * Win * Cout * 2};
+        const cuuint32_t box[5] = {32, 1, (cuuint32_t)Win, 1, (cuuint32_t)(32 / Win)};
         if (!encode(&map_y, y_nhwc, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return "cuTensorMapEncodeTiled failed for the deconv output";
     }
     Params p;
     p.B = B; p.Hin = Hin; p.KB = Cin / BK;
+    p.rows = rows; p.wrows = 32 / Win;
     p.scale = scale; p.shift = shift;
     p.dbg = 0;
 #ifdef IHPR_TIMING_EXPERIMENTS

@@ -395,9 +395,9 @@ def fused_head_soft_argmax(x, weight, bias, joint_num, return_stats=False):
 
 def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
     """relu(batch_norm(conv_transpose2d(x, weight, stride=2, padding=1))) with the BatchNorm in eval mode, as ONE tensor-core kernel
-    (K9, csrc/deconv_bn_relu.cu): the last deconv block of HeadNet at inference (main/model.py:22-38).  x: (B, C_in, H, 32) cuda
-    tensor (made bf16 / channels_last if it is not); weight: the ConvTranspose2d weight (C_in, 256, 4, 4).  Returns the
-    (B, 256, 2 H, 64) bf16 channels_last activation -- the operand fused_head_soft_argmax reads without a copy.  Forward only.
+    (K9, csrc/deconv_bn_relu.cu): the second / third deconv block of HeadNet at inference (main/model.py:22-38).  x: (B, C_in, H, W)
+    cuda tensor with W = 32 (H % 8 == 0) or W = 16 (H % 16 == 0), made bf16 / channels_last if it is not; weight: the ConvTranspose2d
+    weight (C_in, 256, 4, 4).  Returns the (B, 256, 2 H, 2 W) bf16 channels_last activation -- the operand fused_head_soft_argmax reads without a copy.  Forward only.
     The re-laid weights and the folded BatchNorm are cached per (device, stream) until one of the parameter tensors changes
     (storage or in-place version), so a steady inference loop is one launch per call."""
     _require_cuda(x, "x")
@@ -412,7 +412,7 @@ def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps
     params = (weight, bn_weight, bn_bias, running_mean, running_var)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, weight.data_ptr())      # one prepared set per layer
         stamp = tuple((t.data_ptr(), t._version, t.dtype) for t in params) + (float(eps), Cin, Cout)
         entry = _DECONV_PREPARED.get(key)
         if entry is None or entry[0] != stamp:

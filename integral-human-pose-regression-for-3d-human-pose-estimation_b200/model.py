@@ -32,16 +32,22 @@ class HeadNet(nn.Module):
         return self.final_layer(self.deconv_layers(x))
 
     def features(self, x):
-        """deconv_layers(x).  At inference (eval mode, no autograd) the third block -- ConvTranspose2d(256, 256) + BatchNorm + ReLU on a
-        32-wide map -- runs as the tensor-core kernel K9 and lands in the bf16 channels_last layout K3 reads (SURVEY section 8 row N1);
-        everything else, and every other case, is the stock module stack."""
+        """deconv_layers(x).  At inference (eval mode, no autograd) every ConvTranspose2d(·, 256) + BatchNorm + ReLU block whose input
+        map is 16 or 32 wide -- the second and the third block for the reference's 256 x 256 input -- runs as the tensor-core kernel
+        K9 and the last one lands in the bf16 channels_last layout K3 reads; everything else, and every other
+        case, is the stock module stack."""
         dl = self.deconv_layers
-        if (not self.training and not torch.is_grad_enabled() and x.is_cuda and len(dl) == 9 and dl[6].out_channels == 256
-                and dl[6].in_channels % 64 == 0 and x.shape[3] * 4 == 32 and (x.shape[2] * 4) % 8 == 0):
-            y = dl[:6](x)
-            bn = dl[7]
-            return deconv_bn_relu(y, dl[6].weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-        return dl(x)
+        if self.training or torch.is_grad_enabled() or not x.is_cuda:
+            return dl(x)
+        for i in range(0, len(dl), 3):
+            conv, bn = dl[i], dl[i + 1]
+            h, w = x.shape[2], x.shape[3]
+            if (isinstance(conv, nn.ConvTranspose2d) and isinstance(bn, nn.BatchNorm2d) and conv.out_channels == 256 and conv.in_channels % 64 == 0
+                    and conv.in_channels <= 1024 and w in (16, 32) and h % (256 // w) == 0 and bn.track_running_stats and bn.affine):
+                x = deconv_bn_relu(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            else:
+                x = dl[i:i + 3](x)
+        return x
 
     def init_weights(self):                            # model.py:46-56
         for m in self.modules():
