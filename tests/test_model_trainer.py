@@ -159,3 +159,28 @@ def test_sharded_inference_gathers_coordinates_not_heatmaps(built_lib, tmp_path)
     full = torch.arange(5 * 3 * 3, dtype=torch.float32).view(5, 3, 3)
     for r in range(2):
         assert torch.equal(torch.load(out + str(r)), full)
+
+
+def test_head_features_keeps_the_stock_stack_where_k9_does_not_apply(built_lib):
+    """HeadNet.features is deconv_layers(x) bit for bit whenever the tensor-core block (K9: CUDA, eval mode, no autograd, 16- / 32-wide
+    map) does not apply -- on the CPU always; and the C-ABI refuses the shapes K9 cannot do without touching a device."""
+    from ihpr_b200._lib import lib
+    from ihpr_b200.model import get_pose_net
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=4)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3)
+    x = torch.randn(2, 512, 8, 8)
+    net.eval()
+    with torch.no_grad():
+        assert torch.equal(net.head.features(x), net.head.deconv_layers(x))
+    net.train()
+    y = net.head.features(x)
+    assert y.requires_grad and y.shape == (2, 256, 64, 64)
+    L = lib()
+    assert L.ihpr_deconv_bn_relu_workspace_bytes(256, 256) >= 16 * 256 * 256 * 2 + 2 * 256 * 4
+    assert L.ihpr_deconv_bn_relu_workspace_bytes(0, 256) == 0
+    # argument checks come before any CUDA call: bad channel counts / widths / null pointers are reported, not launched
+    assert L.ihpr_deconv_bn_relu(None, None, 1, 256, 256, 32, 32, None, None) < 0
+    assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 128, 32, 32, 256, None) < 0         # C_out must be 256
+    assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 256, 32, 8, 256, None) < 0          # width 8
+    assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 256, 8, 16, 256, None) < 0          # width 16 needs a height that is a multiple of 16
