@@ -9,9 +9,10 @@
 //     TS, two issuing warps                                                K4w ~152 us    K4x ~160 us      (timing build: 164 / 171)
 //     TS, slot ring + N = 64 GEMM2 MMAs (this file)                        K4w 157 us     K4x 194 us       (ncu, cold)
 // Why (profiles/r02_k4_ts_trace.txt, clock64 traces and knock-out builds):
-//   * a tcgen05.mma with M = 128, K = 16 costs ~115-137 clk whatever its N: N = 128 (GEMM1 here) 117 clk, N = 64 from a TMEM A operand
-//     115 clk, N = 256 128-137 clk.  Halving the tile width therefore does not halve GEMM1 -- 16 MMAs per 128 columns cost what 16 MMAs
-//     per 256 columns cost in the shipped form.  MMA time per 128 columns: 1870 + 1100 clk here against 1024 + 1024 there.
+//   * inside this kernel a tcgen05.mma with M = 128, K = 16 cost ~115-137 clk whatever its N: N = 128 (GEMM1 here) 117 clk, N = 64 from a
+//     TMEM A operand 115 clk, N = 256 128-137 clk.  (tools/mma_issue_bench.cu later showed why: one thread needs ~58 clk to ISSUE an MMA,
+//     more next to busy epilogue warps, so MMAs narrower than N = 256 are issue-bound, not pipe-bound.)  Halving the tile width therefore
+//     does not halve GEMM1.  MMA time per 128 columns: 1870 + 1100 clk here against 1024 + 1024 in the shipped form.
 //   * only two tiles fit in shared memory next to the stationary operand, and the per-tile chain  slot free -> load (~1700 clk to the
 //     first k-block) -> GEMM1 -> epilogue (1600 clk) -> GEMM2 -> slot free  is ~6900 clk for two tiles in flight = 3450 clk per tile.
 //   * a lone polling issuer thread needs ~500 clk per poll round next to four busy epilogue warps on its scheduler.
