@@ -6,6 +6,8 @@ runs in lib/libihpr_b200.so.  Semantics follow /root/reference/common/nets/loss.
 import os
 import threading
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -398,8 +400,9 @@ def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps
     (K9, csrc/deconv_bn_relu.cu): the second / third deconv block of HeadNet at inference (main/model.py:22-38).  x: (B, C_in, H, W)
     cuda tensor with W = 32 (H % 8 == 0) or W = 16 (H % 16 == 0), made bf16 / channels_last if it is not; weight: the ConvTranspose2d
     weight (C_in, 256, 4, 4).  Returns the (B, 256, 2 H, 2 W) bf16 channels_last activation -- the operand fused_head_soft_argmax reads without a copy.  Forward only.
-    The re-laid weights and the folded BatchNorm are cached per (device, stream) until one of the parameter tensors changes
-    (storage or in-place version), so a steady inference loop is one launch per call."""
+    The re-laid weights and the folded BatchNorm are cached per (device, stream, weight tensor) for as long as the SAME parameter tensor
+    objects are passed unchanged (identity through weak references + in-place version counters: a module's parameters and buffers), so a
+    steady inference loop is one launch per call; temporaries are prepared every time."""
     _require_cuda(x, "x")
     if x.dim() != 4 or weight.dim() != 4 or tuple(weight.shape[2:]) != (4, 4) or weight.shape[0] != x.shape[1]:
         raise ValueError("x must be (B, C_in, H, W) and weight (C_in, C_out, 4, 4), got %s / %s" % (tuple(x.shape), tuple(weight.shape)))
@@ -412,19 +415,24 @@ def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps
     params = (weight, bn_weight, bn_bias, running_mean, running_var)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, weight.data_ptr())      # one prepared set per layer
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, id(weight))      # one prepared set per layer
         stamp = tuple((t.data_ptr(), t._version, t.dtype) for t in params) + (float(eps), Cin, Cout)
         entry = _DECONV_PREPARED.get(key)
-        if entry is None or entry[0] != stamp:
+        # valid only for the very same tensor OBJECTS, unchanged: a new tensor can land on a recycled address with the same version counter
+        if entry is not None and not (entry[0] == stamp and all(r() is t for r, t in zip(entry[2], params))):
+            entry = None
+        if entry is None:
+            if len(_DECONV_PREPARED) >= 32:             # temporaries as parameters (tests, one-off calls) must not pile up workspaces
+                _DECONV_PREPARED.clear()
             nbytes = lib().ihpr_deconv_bn_relu_workspace_bytes(Cin, Cout)
             if nbytes == 0:
                 raise IhprError("deconv_bn_relu: bad channel counts %d -> %d" % (Cin, Cout))
-            ws = entry[1] if entry is not None and entry[1].numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             wb = weight.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
             g, b_, m, v = (t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in params[1:])
             check(lib().ihpr_deconv_bn_relu_prepare(wb.data_ptr(), g.data_ptr(), b_.data_ptr(), m.data_ptr(), v.data_ptr(), float(eps), Cin, Cout,
                                                     ws.data_ptr(), nbytes, stream))
-            entry = (stamp, ws)
+            entry = (stamp, ws, tuple(weakref.ref(t) for t in params))
             _DECONV_PREPARED[key] = entry
         y = torch.empty((B, Cout, 2 * H, 2 * W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
         check(lib().ihpr_deconv_bn_relu(xb.data_ptr(), entry[1].data_ptr(), B, Cin, Cout, H, W, y.data_ptr(), stream))

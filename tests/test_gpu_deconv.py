@@ -78,12 +78,22 @@ def test_deconv_bn_relu_vs_torch_fp64(case, variant, dev):
     args = [t.to(dev) for t in (gamma, beta, mean, var)]
     with torch.no_grad():
         ya = ihpr_b200.deconv_bn_relu(x.to(dev), wd, *args, eps)
-        stamp = next(iter(functional._DECONV_PREPARED.values()))[0] if len(functional._DECONV_PREPARED) == 1 else None
+        mine = [e for k, e in functional._DECONV_PREPARED.items() if k[2] == id(wd)]
+        assert len(mine) == 1
         yb = ihpr_b200.deconv_bn_relu(x.to(dev), wd, *args, eps)
-        if stamp is not None:
-            assert next(iter(functional._DECONV_PREPARED.values()))[0] == stamp
+        again = [e for k, e in functional._DECONV_PREPARED.items() if k[2] == id(wd)]
+        assert again[0] is mine[0]                      # same tensor objects, unchanged: no second preparation
         args[1].add_(0.25)                              # beta changes in place: the shift must follow
         yc = ihpr_b200.deconv_bn_relu(x.to(dev), wd, *args, eps)
+        assert [e for k, e in functional._DECONV_PREPARED.items() if k[2] == id(wd)][0] is not mine[0]
+        # a DIFFERENT weight tensor that lands on the recycled address of a freed one must not hit the cache (identity, not address)
+        w_other = (wd.float() * 0.5).to(torch.bfloat16)
+        addr = w_other.data_ptr()
+        y_other = ihpr_b200.deconv_bn_relu(x.to(dev), w_other, *args, eps)
+        del w_other
+        w_new = wd.clone()                              # very likely the same address
+        y_new = ihpr_b200.deconv_bn_relu(x.to(dev), w_new, *args, eps)
+        assert torch.equal(y_new, yc) and (w_new.data_ptr() != addr or not torch.equal(y_other, y_new))
     assert torch.equal(ya, y) and torch.equal(yb, y) and not torch.equal(yc, y)
     want_c = torch.relu(F.batch_norm(F.conv_transpose2d(x.to(dev).double(), wd.double(), stride=2, padding=1), mean.to(dev).double(), var.to(dev).double(),
                                      gamma.to(dev).double(), args[1].double(), False, 0.0, eps))
