@@ -81,7 +81,8 @@ class ResPoseNet(nn.Module):
             return fused_head_integral_l1_loss(feat, fl.weight, fl.bias, target["coord"], target["vis"], target["have_depth"])
         if target is None and self.deferred:
             fl = self.head.final_layer
-            return DeferredHeatmap(self.head.deconv_layers(self.backbone(input_img)), fl.weight, fl.bias, self.joint_num)
+            # features(): at inference (eval, no autograd) deconv blocks 2 and 3 run as K9, exactly as in predict()
+            return DeferredHeatmap(self.head.features(self.backbone(input_img)), fl.weight, fl.bias, self.joint_num)
         heatmap = self.head(self.backbone(input_img))
         if target is None:
             return heatmap                             # reference contract, model.py:99-103
