@@ -658,6 +658,9 @@ def train_record(args, dev, world, rank):
                              "roofline_frac": g["roofline"]["frac"], "e2e_value": g["e2e"]["value"]}
     except Exception as e:      # noqa: the eager record stands on its own
         rec["cuda_graph"] = {"error": repr(e)[:300]}
+    g = rec["cuda_graph"]
+    rec["best"] = ({"launch": "cuda_graph", "value": g["value"], "ms_per_step": g["ms_per_step"]} if g.get("value", 0) > rec["value"]
+                   else {"launch": "eager", "value": rec["value"], "ms_per_step": rec["ms_per_step"]})
     return rec
 
 

@@ -411,6 +411,8 @@ def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps
     B, Cin, H, W = x.shape
     Cout = weight.shape[1]
     dev = x.device
+    if B == 0:                                      # an empty batch is an empty result, as with the stock modules
+        return torch.empty((0, Cout, 2 * H, 2 * W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
     xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     params = (weight, bn_weight, bn_bias, running_mean, running_var)
     with torch.cuda.device(dev):

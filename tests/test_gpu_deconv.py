@@ -127,6 +127,8 @@ def test_deconv_rejects_what_the_kernel_cannot_do(dev):
             ihpr_b200.deconv_bn_relu(x.to(dev)[:, :, :4], w.to(dev), *args)                  # height 4
         with pytest.raises(ihpr_b200.IhprError):
             ihpr_b200.deconv_bn_relu(x.to(dev), w.to(dev)[:, :128], *[a[:128] for a in args])    # C_out 128
+    with torch.no_grad():
+        assert ihpr_b200.deconv_bn_relu(x.to(dev)[:0], w.to(dev), *args).shape == (0, 256, 16, 64)    # empty batch: empty result
     with pytest.raises(ihpr_b200.IhprError):                                                   # forward only
         ihpr_b200.deconv_bn_relu(x.to(dev).requires_grad_(True), w.to(dev), *args)
 
