@@ -1,6 +1,7 @@
-// deconv_bn_relu.cu -- K9: the last stage of HeadNet.deconv_layers at inference, ConvTranspose2d(256 -> 256, k4 s2 p1, no bias) +
-// BatchNorm2d (running statistics) + ReLU (/root/reference/main/model.py:22-38 with num_layers = 3: the third block, 32 x 32 -> 64 x 64),
-// as ONE tensor-core kernel that writes the bf16 NHWC activation K3 (head_fused_fwd.cu) reads as its operand -- SURVEY section 8 row N1.
+// deconv_bn_relu.cu -- K9: a deconv block of HeadNet.deconv_layers at inference, ConvTranspose2d(C_in -> 256, k4 s2 p1, no bias) +
+// BatchNorm2d (running statistics) + ReLU (/root/reference/main/model.py:22-38; the second and the third block of the head for the
+// reference's 256 x 256 input: 16 x 16 -> 32 x 32 -> 64 x 64), as ONE tensor-core kernel; the last block writes the bf16 NHWC activation
+// K3 (head_fused_fwd.cu) reads as its operand -- SURVEY section 8 row N1.
 //
 // A stride-2 4x4 transposed convolution is four independent stride-1 2x2 convolutions, one per output phase (py, px) = (oy & 1, ox & 1):
 //     out[b, 2 y0 + py, 2 x0 + px, co] = sum_{ty, tx in {0,1}} sum_ci  x[b, y0 + dy(py, ty), x0 + dx(px, tx), ci] * w[ci, co, ky(py, ty), kx(px, tx)]
@@ -8,7 +9,7 @@
 // i.e. per phase a GEMM  [pixels x (4 taps * C_in)] . [(4 taps * C_in) x C_out]  whose A operand is the input shifted by (dy, dx) -- a
 // plain 4-D TMA box of the NHWC input with out-of-bounds rows / columns zero-filled by the TMA unit (no im2col buffer, no halo code).
 //
-// One work item = (sample, phase, 8 input rows): TWO accumulators of 128 pixels (4 rows x 32) x 256 output channels fill the 512 TMEM
+// One work item = (sample, phase, 8 input rows of a 32-wide map / 16 of a 16-wide one): TWO accumulators of 128 pixels x 256 output channels fill the 512 TMEM
 // columns, so every 32 KiB weight k-block feeds 8 MMAs (the weights are the operand every item re-reads: 512 KiB per accumulator pair).
 // Per k-step (one tap, 64 input channels): A0, A1 = 2 x [128 px x 64] (16 KiB each), B = [256 co x 64] (32 KiB); 16 k-steps per item,
 // 3-stage ring.  Epilogue (16 warps): y = max(0, acc * scale[co] + shift[co]) in fp32 (BatchNorm folded to scale / shift by the prep
@@ -21,7 +22,7 @@
 // stream (knock-out without any loads: -4 %), so clusters of 2 only tie and clusters of 4 lose to cluster scheduling -- the default is
 // CS = 1.  What bounds it: the epilogue cannot overlap the main loop (both accumulators fill tensor memory) and costs ~5.5 k clk per
 // item next to 16.4 k clk of MMAs (profiles/r02_k9_deconv_bench.txt).
-// The last, partial wave of work items is cut into HALF items (one accumulator, 4 input rows) when that shortens the schedule: 512 items
+// The last, partial wave of work items is cut into HALF items (one accumulator) when that shortens the schedule: 512 items
 // on 148 SMs are 3 waves of full items + one wave of 136 halves instead of 4 waves; a batch of 4 is one wave of 128 halves.
 #include "head_tc.cuh"
 
@@ -30,7 +31,7 @@ namespace k9 {
 
 using namespace tc;
 
-constexpr int BM = 128;                 // pixels per accumulator: 4 input rows x 32 columns
+constexpr int BM = 128;                 // pixels per accumulator: 128 / Win input rows x Win columns
 constexpr int BN = 256;                 // output channels (one UMMA N)
 constexpr int BK = 64;
 // input width Win = 32 or 16 (the x extent of the TMA boxes); an accumulator is rows = 128 / Win input rows (4 or 8)
@@ -49,7 +50,7 @@ struct Params {
     int B, Hin, KB;             // KB = C_in / 64
     int rows;                   // input rows per accumulator: 128 / Win
     int wrows;                  // input rows per epilogue warp (32 pixels): 32 / Win
-    int items;                  // cluster items: B * 4 phases * (Hin / 8) / CS
+    int items;                  // cluster items: B * 4 phases * (Hin / (2 * rows)) / CS
     int full_items;             // cluster work units [0, full_items) are whole items; unit full_items + h is half (h & 1) of item full_items + h / 2
     int units;                  // full_items + 2 * (items - full_items)
     const float* scale;         // (256): gamma / sqrt(var + eps)
