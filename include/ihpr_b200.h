@@ -220,6 +220,31 @@ int ihpr_deconv_bn_relu_prepare(const void *weight, const float *gamma, const fl
 int ihpr_deconv_bn_relu(const void *x_nhwc, const void *prepared, int B, int Cin, int Cout, int Hin, int Win,
                         void *y_nhwc, void *stream);
 
+/* The same block in TRAINING (main/model.py:22-38 under main/train.py:64-71): ConvTranspose2d(256, 256, k4, s2, p1, bias=False) +
+ * BatchNorm2d with BATCH statistics + ReLU, forward and backward (csrc/deconv_bn_relu.cu modes kTrain / kDgrad, csrc/bn_train.cu).
+ *   ihpr_deconv_bn_relu_train_fwd (4 launches): re-lays `weight` (C_in, C_out, 4, 4) bf16; the tensor-core GEMM stores the raw
+ *     convolution output y_raw_nhwc (B, 2 Hin, 2 Win, 256) bf16 and accumulates per-channel sums of y, y^2 in its epilogue; a finalize
+ *     launch reduces them in a fixed order (fp64) into saved[0:256] = mean, saved[256:512] = 1 / sqrt(var + eps) (biased variance),
+ *     saved[512:768] = gamma * rstd, saved[768:1024] = beta - mean * scale, and updates running_mean / running_var in place as
+ *     torch.nn.BatchNorm2d does (momentum, unbiased variance; both may be NULL); one streaming pass writes
+ *     out_nhwc = max(0, y_raw * scale + shift) bf16 -- the operand ihpr_head_softargmax_fwd reads.
+ *   ihpr_deconv_bn_relu_train_bwd (4-6 launches): dout_nhwc = d loss / d out (bf16 NHWC) -> dgamma, dbeta (256 fp32 each, fixed-order
+ *     fp64 reduction), dy_raw_nhwc = d loss / d y_raw (bf16 NHWC; the ReLU mask is recomputed from y_raw) and, when dx_nhwc is not NULL,
+ *     dx_nhwc = d loss / d x (B, Hin, Win, 256) bf16 by one tensor-core GEMM (a stride-2 convolution of dy_raw as 16 zero-filled TMA taps).
+ *     The weight gradient is the caller's (a GEMM of x against dy_raw).
+ * `workspace`: ihpr_deconv_train_workspace_bytes bytes, 256-byte aligned, no initialisation; may be shared by forward and backward
+ * calls on one stream.  Same shape rules as ihpr_deconv_bn_relu plus C_in == 256.  Deterministic for a given device. */
+size_t ihpr_deconv_train_workspace_bytes(int Cin, int Cout);
+int ihpr_deconv_bn_relu_train_fwd(const void *x_nhwc, const void *weight, const float *gamma, const float *beta,
+                                  float *running_mean, float *running_var, float momentum, float eps,
+                                  int B, int Cin, int Cout, int Hin, int Win,
+                                  void *y_raw_nhwc, void *out_nhwc, float *saved,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int ihpr_deconv_bn_relu_train_bwd(const void *dout_nhwc, const void *y_raw_nhwc, const void *weight, const float *saved,
+                                  int B, int Cin, int Cout, int Hin, int Win,
+                                  void *dy_raw_nhwc, float *dgamma, float *dbeta, void *dx_nhwc,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in
  * `slices` batch slices pipelined over internal streams, runs forward + backward and copies

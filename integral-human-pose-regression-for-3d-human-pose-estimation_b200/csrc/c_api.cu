@@ -602,6 +602,105 @@ int ihpr_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin
     return IHPR_OK;
 }
 
+// ---- training side of a deconv block: ConvTranspose2d + BatchNorm2d (batch statistics) + ReLU, forward and backward ----
+namespace {
+constexpr int kTrainRowsCap = 1024;         // rows of per-channel partials either reduction may write (4 per SM)
+struct TrainWs {
+    size_t off_wp_fwd, off_wp_dgrad, off_part, off_cP, off_cQ, total;
+};
+TrainWs train_ws(int Cin, int Cout) {
+    TrainWs l;
+    const size_t wbytes = align_up((size_t)16 * Cin * Cout * 2, 256);
+    l.off_wp_fwd = 0;
+    l.off_wp_dgrad = wbytes;
+    l.off_part = 2 * wbytes;
+    l.off_cP = l.off_part + (size_t)kTrainRowsCap * 2 * Cout * sizeof(float);
+    l.off_cQ = l.off_cP + align_up((size_t)Cout * sizeof(float), 256);
+    l.total = l.off_cQ + align_up((size_t)Cout * sizeof(float), 256);
+    return l;
+}
+int deconv_train_check(int B, int Cin, int Cout, int Hin, int Win) {
+    if (B <= 0) return fail(IHPR_EINVAL, "non-positive batch");
+    if (Cin != 256 || Cout != 256) return fail(IHPR_EINVAL, "the training deconv block needs C_in == C_out == 256 (got %d -> %d)", Cin, Cout);
+    if ((Win != 32 && Win != 16) || Hin <= 0 || Hin % (256 / Win) != 0)
+        return fail(IHPR_EINVAL, "the training deconv block needs an input of width 32 (height %% 8 == 0) or 16 (height %% 16 == 0), got %dx%d", Hin, Win);
+    if ((long long)B * Hin > 0x7fffffffLL / 4) return fail(IHPR_EINVAL, "B*H does not fit");
+    return IHPR_OK;
+}
+}  // namespace
+
+size_t ihpr_deconv_train_workspace_bytes(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0) return 0;
+    return train_ws(Cin, Cout).total;
+}
+
+int ihpr_deconv_bn_relu_train_fwd(const void* x_nhwc, const void* weight, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  float momentum, float eps, int B, int Cin, int Cout, int Hin, int Win, void* y_raw_nhwc, void* out_nhwc, float* saved,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!x_nhwc || !weight || !gamma || !beta || !y_raw_nhwc || !out_nhwc || !saved || !workspace) return fail(IHPR_EINVAL, "null argument");
+    if ((running_mean == nullptr) != (running_var == nullptr)) return fail(IHPR_EINVAL, "running_mean and running_var come together (or both NULL)");
+    int rc = deconv_train_check(B, Cin, Cout, Hin, Win);
+    if (rc) return rc;
+    if (!(eps >= 0.f)) return fail(IHPR_EINVAL, "eps must be non-negative");
+    if (((uintptr_t)x_nhwc | (uintptr_t)weight | (uintptr_t)y_raw_nhwc | (uintptr_t)out_nhwc | (uintptr_t)saved) & 15)
+        return fail(IHPR_EINVAL, "x / weight / y_raw / out / saved must be 16-byte aligned");
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    const TrainWs l = train_ws(Cin, Cout);
+    if (workspace_bytes < l.total) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, l.total);
+    int num_sms = 0;
+    rc = check_device(x_nhwc, &num_sms);
+    if (rc) return rc;
+    if (4 * num_sms > kTrainRowsCap) return fail(IHPR_EINVAL, "%d SMs exceed the partial-row capacity of the workspace", num_sms);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* w8 = static_cast<char*>(workspace);
+    float* part = reinterpret_cast<float*>(w8 + l.off_part);
+    float *mean = saved, *rstd = saved + Cout, *scale = saved + 2 * Cout, *shift = saved + 3 * Cout;
+    int launches = 0, rows = 0;
+    ihpr::launch_deconv_relayout(weight, Cin, Cout, w8 + l.off_wp_fwd, nullptr, &launches, s);
+    const char* err = ihpr::launch_deconv_train_fwd(x_nhwc, w8 + l.off_wp_fwd, B, Cin, Cout, Hin, Win, y_raw_nhwc, part, &rows, num_sms, &launches, s);
+    if (err) return fail(IHPR_ECUDA, "%s", err);
+    const size_t n_pix = (size_t)B * 4 * Hin * Win;
+    ihpr::launch_bn_stat_finalize(part, rows, n_pix, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, &launches, s);
+    ihpr::launch_bn_relu_apply(y_raw_nhwc, out_nhwc, n_pix, scale, shift, num_sms, &launches, s);
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
+int ihpr_deconv_bn_relu_train_bwd(const void* dout_nhwc, const void* y_raw_nhwc, const void* weight, const float* saved, int B, int Cin, int Cout, int Hin, int Win,
+                                  void* dy_raw_nhwc, float* dgamma, float* dbeta, void* dx_nhwc, void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!dout_nhwc || !y_raw_nhwc || !saved || !dy_raw_nhwc || !dgamma || !dbeta || !workspace) return fail(IHPR_EINVAL, "null argument");
+    if (dx_nhwc && !weight) return fail(IHPR_EINVAL, "the input gradient needs the weight");
+    int rc = deconv_train_check(B, Cin, Cout, Hin, Win);
+    if (rc) return rc;
+    if (((uintptr_t)dout_nhwc | (uintptr_t)y_raw_nhwc | (uintptr_t)weight | (uintptr_t)dy_raw_nhwc | (uintptr_t)dx_nhwc | (uintptr_t)saved) & 15)
+        return fail(IHPR_EINVAL, "dout / y_raw / weight / dy_raw / dx / saved must be 16-byte aligned");
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    const TrainWs l = train_ws(Cin, Cout);
+    if (workspace_bytes < l.total) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, l.total);
+    int num_sms = 0;
+    rc = check_device(dout_nhwc, &num_sms);
+    if (rc) return rc;
+    if (ihpr::bn_bwd_rows(num_sms) > kTrainRowsCap) return fail(IHPR_EINVAL, "%d SMs exceed the partial-row capacity of the workspace", num_sms);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* w8 = static_cast<char*>(workspace);
+    const float *mean = saved, *rstd = saved + Cout, *scale = saved + 2 * Cout, *shift = saved + 3 * Cout;
+    int launches = 0;
+    if (dx_nhwc) ihpr::launch_deconv_relayout(weight, Cin, Cout, nullptr, w8 + l.off_wp_dgrad, &launches, s);
+    const size_t n_pix = (size_t)B * 4 * Hin * Win;
+    ihpr::launch_bn_relu_bwd(dout_nhwc, y_raw_nhwc, dy_raw_nhwc, n_pix, scale, shift, mean, rstd, dgamma, dbeta, reinterpret_cast<float*>(w8 + l.off_part),
+                             reinterpret_cast<float*>(w8 + l.off_cP), reinterpret_cast<float*>(w8 + l.off_cQ), num_sms, &launches, s);
+    if (dx_nhwc) {
+        const char* err = ihpr::launch_deconv_dgrad(dy_raw_nhwc, w8 + l.off_wp_dgrad, B, Cin, Cout, Hin, Win, dx_nhwc, num_sms, &launches, s);
+        if (err) return fail(IHPR_ECUDA, "%s", err);
+    }
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
                                   const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
                                   int device, int slices) {

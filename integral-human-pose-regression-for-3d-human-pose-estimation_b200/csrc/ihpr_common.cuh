@@ -401,5 +401,17 @@ void launch_deconv_prepare(const void* weight, const float* gamma, const float* 
                            void* workspace, int* launches, cudaStream_t s);
 const char* launch_deconv_bn_relu(const void* x_nhwc, const void* prepared, int B, int Cin, int Cout, int Hin, int Win, void* y_nhwc, int num_sms, int cluster,
                                   int* launches, cudaStream_t s);
+// training side of the deconv block (deconv_bn_relu.cu MODE kTrain / kDgrad, bn_train.cu)
+void launch_deconv_relayout(const void* weight, int Cin, int Cout, void* wp_fwd, void* wp_dgrad, int* launches, cudaStream_t s);
+const char* launch_deconv_train_fwd(const void* x_nhwc, const void* wp_fwd, int B, int Cin, int Cout, int Hin, int Win, void* y_raw_nhwc, float* stat_part,
+                                    int* stat_rows, int num_sms, int* launches, cudaStream_t s);
+const char* launch_deconv_dgrad(const void* dy_nhwc, const void* wp_dgrad, int B, int Cin, int Cout, int Hin, int Win, void* dx_nhwc, int num_sms, int* launches,
+                                cudaStream_t s);
+int bn_bwd_rows(int num_sms);
+void launch_bn_stat_finalize(const float* part, int rows, size_t n_per_channel, const float* gamma, const float* beta, float eps, float momentum,
+                             float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int* launches, cudaStream_t s);
+void launch_bn_relu_apply(const void* y, void* out, size_t n_pix, const float* scale, const float* shift, int num_sms, int* launches, cudaStream_t s);
+void launch_bn_relu_bwd(const void* dout, const void* y, void* dy, size_t n_pix, const float* scale, const float* shift, const float* mean, const float* rstd,
+                        float* dgamma, float* dbeta, float* part, float* cP, float* cQ, int num_sms, int* launches, cudaStream_t s);
 
 }  // namespace ihpr

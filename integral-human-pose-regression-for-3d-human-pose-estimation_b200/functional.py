@@ -444,6 +444,92 @@ def deconv_bn_relu(x, weight, bn_weight, bn_bias, running_mean, running_var, eps
 _DECONV_PREPARED = {}
 
 
+def _nhwc_bf16(t):
+    """(B, C, H, W) tensor -> bf16 with channels_last strides, i.e. physically (B, H, W, C) dense; no copy when it already is."""
+    return t.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+class _DeconvBnReluTrain(torch.autograd.Function):
+    """One deconv block of HeadNet in training (main/model.py:22-38): ConvTranspose2d(256, 256, k4, s2, p1, bias=False) + BatchNorm2d with
+    batch statistics + ReLU.  Forward: the K9 GEMM in its training mode (raw output + per-channel sums from the epilogue), a finalize launch,
+    one normalise + ReLU pass.  Backward: BatchNorm + ReLU backward in two streaming passes (K10), the input gradient as one tensor-core GEMM
+    (K9, mode kDgrad); the weight gradient is a library GEMM for now (aten convolution_backward on the bf16 operands).
+    Saved for backward: the bf16 input, the bf16 raw convolution output and 4 x 256 floats."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, momentum, eps):
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[1]
+        dev = x.device
+        xb = _nhwc_bf16(x)
+        wb = weight.detach().to(torch.bfloat16).contiguous()
+        g = gamma.detach().to(torch.float32).contiguous()
+        b_ = beta.detach().to(torch.float32).contiguous()
+        for t, n in ((running_mean, "running_mean"), (running_var, "running_var")):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev):
+                raise IhprError("%s must be a contiguous fp32 tensor on %s (it is updated in place)" % (n, dev))
+        L = lib()
+        y_raw = torch.empty((B, Cout, 2 * H, 2 * W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        out = torch.empty_like(y_raw)
+        saved = torch.empty((4, Cout), dtype=torch.float32, device=dev)
+        nbytes = L.ihpr_deconv_train_workspace_bytes(Cin, Cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with _on_device(dev) as stream:
+            check(L.ihpr_deconv_bn_relu_train_fwd(xb.data_ptr(), wb.data_ptr(), g.data_ptr(), b_.data_ptr(),
+                                                  running_mean.data_ptr() if running_mean is not None else None,
+                                                  running_var.data_ptr() if running_var is not None else None, float(momentum), float(eps),
+                                                  B, Cin, Cout, H, W, y_raw.data_ptr(), out.data_ptr(), saved.data_ptr(), ws.data_ptr(), nbytes, stream))
+        if running_mean is not None:
+            # written through raw pointers: tell autograd (and K9's prepared-parameter cache, which stamps the version counters)
+            torch.autograd.graph.increment_version(running_mean)
+            torch.autograd.graph.increment_version(running_var)
+        ctx.save_for_backward(xb, wb, y_raw, saved)
+        ctx.meta = (x.dtype, weight.dtype, gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xb, wb, y_raw, saved = ctx.saved_tensors
+        x_dtype, w_dtype, g_dtype, b_dtype = ctx.meta
+        B, Cin, H, W = xb.shape
+        Cout = wb.shape[1]
+        dev = xb.device
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        L = lib()
+        go = _nhwc_bf16(grad_out)
+        dy = torch.empty_like(y_raw)
+        dgb = torch.empty((2, Cout), dtype=torch.float32, device=dev)
+        dx = torch.empty((B, Cin, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) if need_x else None
+        nbytes = L.ihpr_deconv_train_workspace_bytes(Cin, Cout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with _on_device(dev) as stream:
+            check(L.ihpr_deconv_bn_relu_train_bwd(go.data_ptr(), y_raw.data_ptr(), wb.data_ptr(), saved.data_ptr(), B, Cin, Cout, H, W, dy.data_ptr(),
+                                                  dgb[0].data_ptr(), dgb[1].data_ptr(), dx.data_ptr() if dx is not None else None,
+                                                  ws.data_ptr(), nbytes, stream))
+        dw = None
+        if need_w:
+            # weight gradient: x^T . dy per tap -- the one GEMM of this block still left to the library
+            dw = torch.ops.aten.convolution_backward(dy, xb, wb, None, [2, 2], [1, 1], [1, 1], True, [0, 0], 1, [False, True, False])[1].to(w_dtype)
+        return (dx.to(x_dtype) if dx is not None else None, dw, dgb[0].to(g_dtype) if ctx.needs_input_grad[2] else None,
+                dgb[1].to(b_dtype) if ctx.needs_input_grad[3] else None, None, None, None, None)
+
+
+def deconv_bn_relu_train(x, weight, bn_weight, bn_bias, running_mean=None, running_var=None, momentum=0.1, eps=1e-5):
+    """relu(batch_norm(conv_transpose2d(x, weight, stride=2, padding=1), training=True)) for the 256 -> 256 deconv blocks of HeadNet
+    (main/model.py:22-38) with autograd: the forward GEMM (tcgen05) produces the batch statistics in its epilogue, BatchNorm + ReLU and
+    their backward are streaming kernels, the input gradient is a second tcgen05 GEMM.  x: (B, 256, H, W) cuda tensor with W = 32
+    (H % 8 == 0) or W = 16 (H % 16 == 0); returns the (B, 256, 2 H, 2 W) bf16 channels_last activation.  ``running_mean`` / ``running_var``
+    (fp32) are updated in place like torch.nn.BatchNorm2d does; the caller increments ``num_batches_tracked``."""
+    _require_cuda(x, "x")
+    if x.dim() != 4 or weight.dim() != 4 or tuple(weight.shape[2:]) != (4, 4) or weight.shape[0] != x.shape[1]:
+        raise ValueError("x must be (B, C_in, H, W) and weight (C_in, C_out, 4, 4), got %s / %s" % (tuple(x.shape), tuple(weight.shape)))
+    if x.shape[0] == 0:
+        raise ValueError("batch statistics of an empty batch do not exist")
+    if momentum is None:
+        raise ValueError("momentum=None (cumulative moving average) is not supported by the fused block")
+    return _DeconvBnReluTrain.apply(x, weight, bn_weight, bn_bias, running_mean, running_var, momentum, eps)
+
+
 class _FusedHeadIntegralL1(torch.autograd.Function):
     """final_layer (1x1 conv) + soft-argmax + L1 loss with the heat-map living only in TMEM: K3 forward; K4w / K4x backward
     (dW, dbias, dX in-kernel -- no heat-map gradient in HBM, no library GEMM).

@@ -10,7 +10,7 @@ sm_100a path (what main/train.py:64-67 does in two calls).
 import torch
 import torch.nn as nn
 
-from .functional import DeferredHeatmap, deconv_bn_relu, flip_merge, fused_head_integral_l1_loss, fused_head_soft_argmax
+from .functional import DeferredHeatmap, deconv_bn_relu, deconv_bn_relu_train, flip_merge, fused_head_integral_l1_loss, fused_head_soft_argmax
 from .nets.loss import JointLocationLoss, soft_argmax
 from .nets.resnet import ResNetBackbone
 
@@ -31,20 +31,30 @@ class HeadNet(nn.Module):
     def forward(self, x):
         return self.final_layer(self.deconv_layers(x))
 
-    def features(self, x):
+    def features(self, x, fused_training=False):
         """deconv_layers(x).  At inference (eval mode, no autograd) every ConvTranspose2d(·, 256) + BatchNorm + ReLU block whose input
         map is 16 or 32 wide -- the second and the third block for the reference's 256 x 256 input -- runs as the tensor-core kernel
-        K9 and the last one lands in the bf16 channels_last layout K3 reads; everything else, and every other
-        case, is the stock module stack."""
+        K9 and the last one lands in the bf16 channels_last layout K3 reads.  With ``fused_training=True`` the
+        same blocks (256 -> 256 channels) run in TRAINING mode through ``deconv_bn_relu_train`` (K9's training forward with batch statistics
+        from the epilogue, K10 BatchNorm / ReLU passes, K9's input-gradient GEMM).  Everything else, and every other case, is the stock
+        module stack."""
         dl = self.deconv_layers
-        if self.training or torch.is_grad_enabled() or not x.is_cuda:
+        infer = not self.training and not torch.is_grad_enabled()
+        train = bool(fused_training) and self.training and torch.is_grad_enabled()
+        if not x.is_cuda or not (infer or train):
             return dl(x)
         for i in range(0, len(dl), 3):
             conv, bn = dl[i], dl[i + 1]
             h, w = x.shape[2], x.shape[3]
-            if (isinstance(conv, nn.ConvTranspose2d) and isinstance(bn, nn.BatchNorm2d) and conv.out_channels == 256 and conv.in_channels % 64 == 0
-                    and conv.in_channels <= 1024 and w in (16, 32) and h % (256 // w) == 0 and bn.track_running_stats and bn.affine):
+            ok = (isinstance(conv, nn.ConvTranspose2d) and isinstance(bn, nn.BatchNorm2d) and conv.out_channels == 256 and conv.in_channels % 64 == 0
+                  and conv.in_channels <= 1024 and w in (16, 32) and h % (256 // w) == 0 and bn.affine)
+            if ok and infer and bn.track_running_stats:
                 x = deconv_bn_relu(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            elif ok and train and conv.in_channels == 256 and x.shape[0] > 0 and bn.momentum is not None:
+                x = deconv_bn_relu_train(x, conv.weight, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                                         bn.running_var if bn.track_running_stats else None, bn.momentum, bn.eps)
+                if bn.track_running_stats and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
             else:
                 x = dl[i:i + 3](x)
         return x
@@ -61,7 +71,7 @@ class HeadNet(nn.Module):
 
 
 class ResPoseNet(nn.Module):
-    def __init__(self, backbone, head, joint_num=None, fused_head=False, deferred=False):
+    def __init__(self, backbone, head, joint_num=None, fused_head=False, deferred=False, fused_deconv=None):
         """fused_head=True: final_layer + soft-argmax (+ loss) run as the tensor-core kernels K3 / K4 and the
         (B, J*D, H, W) heat-map is never stored (same parameters, same checkpoints).
         deferred=True (with fused_head): ``forward(img)`` without a target returns a ``DeferredHeatmap`` instead of the tensor, so
@@ -72,17 +82,19 @@ class ResPoseNet(nn.Module):
         self.joint_num = joint_num
         self.fused_head = fused_head
         self.deferred = bool(deferred and fused_head)
+        # training: deconv blocks 2 and 3 through K9 / K10 (row N1); default = wherever the fused head is used
+        self.fused_deconv = fused_head if fused_deconv is None else bool(fused_deconv and fused_head)
         self.criterion = JointLocationLoss()
 
     def forward(self, input_img, target=None):
         if target is not None and self.fused_head:
-            feat = self.head.deconv_layers(self.backbone(input_img))
+            feat = self.head.features(self.backbone(input_img), fused_training=self.fused_deconv)
             fl = self.head.final_layer
             return fused_head_integral_l1_loss(feat, fl.weight, fl.bias, target["coord"], target["vis"], target["have_depth"])
         if target is None and self.deferred:
             fl = self.head.final_layer
             # features(): at inference (eval, no autograd) deconv blocks 2 and 3 run as K9, exactly as in predict()
-            return DeferredHeatmap(self.head.features(self.backbone(input_img)), fl.weight, fl.bias, self.joint_num)
+            return DeferredHeatmap(self.head.features(self.backbone(input_img), fused_training=self.fused_deconv), fl.weight, fl.bias, self.joint_num)
         heatmap = self.head(self.backbone(input_img))
         if target is None:
             return heatmap                             # reference contract, model.py:99-103
@@ -146,11 +158,11 @@ class GraphedPredict:
         return self.static_out
 
 
-def get_pose_net(cfg, is_train, joint_num, fused_head=False, deferred=False):
+def get_pose_net(cfg, is_train, joint_num, fused_head=False, deferred=False, fused_deconv=None):
     """model.py:105-114.  `cfg` needs `resnet_type` and `depth_dim` (main/config.py:24,28)."""
     backbone = ResNetBackbone(cfg.resnet_type)
     head = HeadNet(joint_num, depth_dim=cfg.depth_dim, inplanes=backbone.out_channels)
     if is_train:
         backbone.init_weights()
         head.init_weights()
-    return ResPoseNet(backbone, head, joint_num, fused_head=fused_head, deferred=deferred)
+    return ResPoseNet(backbone, head, joint_num, fused_head=fused_head, deferred=deferred, fused_deconv=fused_deconv)
