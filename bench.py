@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--unfused-loss", action="store_true", help="train workload: K1 + K2 instead of K5")
     ap.add_argument("--fused-head", action="store_true", help="train workload: final_layer + loss as K3/K4 (heat-map never stored)")
+    ap.add_argument("--stock-deconv", action="store_true", help="train workload with --fused-head: keep deconv blocks 2 / 3 on cuDNN + torch BatchNorm "
+                                                                "(comparison arm; default: K9 / K10 training kernels, row N1)")
     ap.add_argument("--cuda-graph", action="store_true", help="train workload, 1 GPU: replay the whole step as one CUDA graph")
     ap.add_argument("--torch-loss", action="store_true", help="train workload: the reference's eager torch loss on the GPU (comparison arm)")
     ap.add_argument("--no-train", action="store_true", help="path workload: skip the `train` sub-record (ResNet-50 training step, BASELINE configs[1-3])")
@@ -541,7 +543,8 @@ def train_core(args, dev, world, rank, resnet, fused_head, crit_kind, cuda_graph
     cfg = types.SimpleNamespace(resnet_type=resnet, depth_dim=args.depth, input_shape=(4 * args.hw, 4 * args.hw),
                                 output_shape=(args.hw, args.hw), lr=1e-3, lr_dec_epoch=[210, 280], lr_dec_factor=0.1, batch_size=B)
     torch.manual_seed(0)
-    net = get_pose_net(cfg, True, J, fused_head=fused_head)
+    fused_deconv = bool(fused_head and not getattr(args, "stock_deconv", False))
+    net = get_pose_net(cfg, True, J, fused_head=fused_head, fused_deconv=fused_deconv)
     crit = None
     if crit_kind == "torch":
         crit = EagerJointLocationLoss()          # comparison arm only: the reference's eager op sequence on the GPU
@@ -623,7 +626,8 @@ def train_core(args, dev, world, rank, resnet, fused_head, crit_kind, cuda_graph
                                "DDP NCCL all-reduce" % (resnet, 4 * args.hw, 4 * args.hw, B, J, args.depth),
                    "criterion": {"torch": "torch eager (reference ops)", "unfused": "ihpr_b200 K1+K2", "k5": "ihpr_b200 K5 (one launch)",
                                  "head": "ihpr_b200 final_layer + criterion fused on tcgen05 (heat-map never stored)"}[crit_kind],
-                   "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark",
+                   "backbone_head": "stock PyTorch/cuDNN, channels_last, cudnn.benchmark" + (
+                       "; deconv blocks 2 / 3 (ConvTranspose2d + BatchNorm + ReLU, forward and backward) on K9 / K10, their weight gradient on cuDNN" if fused_deconv else ""),
                    "launch": "one CUDA graph per step" if cuda_graph else "eager"},
         "clocks": clocks,
         "e2e": {"value": world * B / wall_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": wall_e2e * 1e3,

@@ -207,15 +207,37 @@ def test_autograd_block_vs_torch_fp64_autograd(dev):
     want.backward(dout.double())
 
     def rel(a, b):
-        return float((a.double() - b).norm() / b.norm())
+        return float((a.detach().double() - b.detach()).norm() / b.detach().norm())
 
     assert rel(out, want) <= 2.0 ** -7
     assert rel(xs.grad, x64.grad) <= 2e-2, rel(xs.grad, x64.grad)
     assert rel(ws_.grad, w64.grad) <= 2e-2, rel(ws_.grad, w64.grad)
-    assert rel(gs.grad, g64.grad) <= 1e-2, rel(gs.grad, g64.grad)
-    assert rel(bs.grad, b64.grad) <= 1e-2, rel(bs.grad, b64.grad)
+    # dgamma / dbeta are sums of ~16 k masked N(0, 1) values per channel (|sum| ~ 90): the ~1e-3 of the elements whose pre-activation lies within
+    # the bf16 rounding of y_raw of zero flip their mask, each moving the sum by ~1 -- 1.5e-2 of the norm (measured), the same for ANY bf16 block
+    assert rel(gs.grad, g64.grad) <= 3e-2, rel(gs.grad, g64.grad)
+    assert rel(bs.grad, b64.grad) <= 3e-2, rel(bs.grad, b64.grad)
     assert xs.grad.dtype == torch.float32 and ws_.grad.shape == w.shape
     assert float(rm.abs().max()) > 0 and rm._version > 0           # updated in place, version bumped for the inference cache
+
+
+def test_training_block_into_fused_head_vs_oracle_soft_argmax(dev):
+    """VERDICT r1 #6's check: the training-mode block feeding K3 (final_layer + soft-argmax on tcgen05) against torch's fp64
+    ConvTranspose2d + BatchNorm (batch statistics) + ReLU -> fp64 1x1 conv -> the oracle's soft-argmax (oracle/truth64.c)."""
+    import ihpr_b200
+    from oracle import truth
+    B, J, D = 2, 18, 64
+    x, w, gamma, beta = _problem(B, 32, 32, seed=21, dev=dev)
+    g = torch.Generator().manual_seed(4)
+    wt = (torch.randn(J * D, 256, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(J * D, generator=g) * 0.5).to(dev)
+    with torch.no_grad():
+        feat = ihpr_b200.deconv_bn_relu_train(x, w, gamma, beta, None, None, momentum=0.1, eps=EPS)
+        coords = ihpr_b200.fused_head_soft_argmax(feat, wt, bias, J)
+        f64 = torch.relu(F.batch_norm(F.conv_transpose2d(x.double(), w.double(), stride=2, padding=1), None, None, gamma.double(), beta.double(), True, 0.0, EPS))
+        heat = F.conv2d(f64, wt.double().view(J * D, 256, 1, 1), bias.double())
+    c64 = truth.soft_argmax_f64(heat.cpu().numpy(), J)[0]
+    # the features carry two bf16 roundings (2^-8 relative): the heat-map moves by ~1e-2, the expectation over 64^3 voxels by a few 1e-3 voxel
+    assert float(np.abs(coords.cpu().numpy() - c64).max()) <= 2e-2
 
 
 def test_training_entries_reject_what_they_cannot_do(dev):
