@@ -40,20 +40,20 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// 8 CTAs x 1024 threads: thread = (channel c of the CTA's 32, row slice sl of 32); rows are summed in fp64 in a fixed order
-constexpr int FSL = 32;
+// 16 CTAs x 1024 threads: thread = (channel c of the CTA's 16, row slice sl of 64); rows are summed in fp64 in a fixed order
+constexpr int FSL = 64, FCH = 16;
 template <bool BWD>
-__global__ void __launch_bounds__(32 * FSL) finalize_kernel(const float* __restrict__ part, int rows, double inv_n, double unbias, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(FCH * FSL) finalize_kernel(const float* __restrict__ part, int rows, double inv_n, double unbias, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                                        float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                        float* __restrict__ scale, float* __restrict__ shift,
                                                        // BWD: inputs mean / rstd / scale(= gamma * rstd), outputs dgamma, dbeta and the constants P, Q of bwd_apply
                                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cP, float* __restrict__ cQ) {
-    __shared__ double sh[2][FSL][32];
-    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    __shared__ double sh[2][FSL][FCH];
+    const int cl = threadIdx.x % FCH, sl = threadIdx.x / FCH;
+    const int c = blockIdx.x * FCH + cl;
     double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = sl; r < rows; r += FSL) {
         s0 += (double)__ldg(part + (size_t)r * 2 * C + c);
         s1 += (double)__ldg(part + (size_t)r * 2 * C + C + c);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const uint4* __restr
 }
 
 // partial sums of dz = dout * [y * scale + shift > 0] and dz * y; one row [2][256] per CTA, pixel lanes added in lane order
-__global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y, size_t n_pix,
+__global__ void __launch_bounds__(256, 4) bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y, size_t n_pix,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ part) {
     __shared__ float sm[8][2 * C];
     const int oct = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -208,19 +208,28 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const uint4* __r
 }  // namespace k10
 
 // ---- host side --------------------------------------------------------------------------------------------------
-// rows of partials the backward reduction writes (one per CTA)
+// The streaming kernels are grid-stride loops with equal shares per CTA: the grid is exactly the number of CTAs that are resident at once
+// (a partial second wave would run at a fraction of the memory parallelism and roughly double the time -- measured with the first version).
+template <typename K>
+static int resident_ctas(K kern, int num_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * num_sms;
+}
+// rows of partials the backward reduction writes (one per CTA): 4 CTAs of 256 threads per SM (__launch_bounds__(256, 4))
 int bn_bwd_rows(int num_sms) { return 4 * num_sms; }
 
 void launch_bn_stat_finalize(const float* part, int rows, size_t n_per_channel, const float* gamma, const float* beta, float eps, float momentum,
                              float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int* launches, cudaStream_t s) {
     const double n = (double)n_per_channel;
-    k10::finalize_kernel<false><<<k10::C / 32, 32 * k10::FSL, 0, s>>>(part, rows, 1.0 / n, n > 1.0 ? n / (n - 1.0) : 1.0, gamma, beta, eps, momentum, running_mean, running_var,
+    k10::finalize_kernel<false><<<k10::C / k10::FCH, k10::FCH * k10::FSL, 0, s>>>(part, rows, 1.0 / n, n > 1.0 ? n / (n - 1.0) : 1.0, gamma, beta, eps, momentum, running_mean, running_var,
                                                            mean, rstd, scale, shift, nullptr, nullptr, nullptr, nullptr);
     ++*launches;
 }
 
 void launch_bn_relu_apply(const void* y, void* out, size_t n_pix, const float* scale, const float* shift, int num_sms, int* launches, cudaStream_t s) {
-    k10::bn_relu_apply_kernel<<<8 * num_sms, 256, 0, s>>>(static_cast<const uint4*>(y), static_cast<uint4*>(out), n_pix, scale, shift);
+    static const int grid = resident_ctas(k10::bn_relu_apply_kernel, num_sms);
+    k10::bn_relu_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(y), static_cast<uint4*>(out), n_pix, scale, shift);
     ++*launches;
 }
 
@@ -229,9 +238,10 @@ void launch_bn_relu_bwd(const void* dout, const void* y, void* dy, size_t n_pix,
                         float* dgamma, float* dbeta, float* part, float* cP, float* cQ, int num_sms, int* launches, cudaStream_t s) {
     const int rows = bn_bwd_rows(num_sms);
     k10::bn_relu_bwd_reduce_kernel<<<rows, 256, 0, s>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), n_pix, scale, shift, part);
-    k10::finalize_kernel<true><<<k10::C / 32, 32 * k10::FSL, 0, s>>>(part, rows, 1.0 / (double)n_pix, 1.0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
+    k10::finalize_kernel<true><<<k10::C / k10::FCH, k10::FCH * k10::FSL, 0, s>>>(part, rows, 1.0 / (double)n_pix, 1.0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr,
                                                           const_cast<float*>(mean), const_cast<float*>(rstd), const_cast<float*>(scale), nullptr, dgamma, dbeta, cP, cQ);
-    k10::bn_relu_bwd_apply_kernel<<<8 * num_sms, 256, 0, s>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), static_cast<uint4*>(dy), n_pix, scale,
+    static const int grid = resident_ctas(k10::bn_relu_bwd_apply_kernel, num_sms);
+    k10::bn_relu_bwd_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), static_cast<uint4*>(dy), n_pix, scale,
                                                               shift, cP, cQ);
     *launches += 3;
 }
