@@ -263,11 +263,14 @@ def test_full_size_properties_and_determinism(dev):
     with torch.no_grad():
         c_shift = ihpr_b200.soft_argmax(h.detach() + 3.0, J)
     assert (c_shift - c1).abs().max().item() <= 2e-3
-    # oracle on the first and last sample
+    # oracle on the first and last sample: coordinates AND the heat-map gradient (a one-sample problem's gradient is B times the
+    # batch's: the loss is a mean over B * J joint terms, loss.py:52)
+    gt_n, vis_n, hd_n = gt.cpu().numpy(), vis.cpu().numpy(), hd.cpu().numpy()
     for b in (0, B - 1):
         hb = h.detach()[b:b + 1].cpu().numpy()
-        c64, m, l = truth.soft_argmax_f64(hb, J)
+        _, c64, g64 = truth.fwd_bwd_f64(hb, gt_n[b:b + 1], vis_n[b:b + 1], hd_n[b:b + 1])
         assert coord_err(c1[b:b + 1].cpu().numpy(), c64) <= TOL
+        assert grad_err(g1[b:b + 1].cpu().numpy(), g64 / B) <= TOL
     # all variants agree to rounding on the full size
     for v in (11, 2):
         ihpr_b200.set_variant(v)
