@@ -231,7 +231,7 @@ int ihpr_deconv_bn_relu(const void *x_nhwc, const void *prepared, int B, int Cin
  *   ihpr_deconv_bn_relu_train_bwd (4-6 launches): dout_nhwc = d loss / d out (bf16 NHWC) -> dgamma, dbeta (256 fp32 each, fixed-order
  *     fp64 reduction), dy_raw_nhwc = d loss / d y_raw (bf16 NHWC; the ReLU mask is recomputed from y_raw) and, when dx_nhwc is not NULL,
  *     dx_nhwc = d loss / d x (B, Hin, Win, 256) bf16 by one tensor-core GEMM (a stride-2 convolution of dy_raw as 16 zero-filled TMA taps).
- *     The weight gradient is the caller's (a GEMM of x against dy_raw).
+ *     The weight gradient is ihpr_deconv_wgrad's (x against dy_raw).
  * `workspace`: ihpr_deconv_train_workspace_bytes bytes, 256-byte aligned, no initialisation; may be shared by forward and backward
  * calls on one stream.  Same shape rules as ihpr_deconv_bn_relu plus C_in == 256.  Deterministic for a given device. */
 size_t ihpr_deconv_train_workspace_bytes(int Cin, int Cout);
@@ -244,6 +244,15 @@ int ihpr_deconv_bn_relu_train_bwd(const void *dout_nhwc, const void *y_raw_nhwc,
                                   int B, int Cin, int Cout, int Hin, int Win,
                                   void *dy_raw_nhwc, float *dgamma, float *dbeta, void *dx_nhwc,
                                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* The weight gradient of the same block (csrc/deconv_wgrad.cu, K11): dweight (C_in, C_out, 4, 4) fp32 (the layout of
+ * ConvTranspose2d.weight) = sum over the batch of x^T . dy per tap, 16 tensor-core GEMMs whose contraction runs over the pixels (both operands
+ * are the pixel-major TMA boxes of the NHWC tensors, read as MN-major UMMA operands); the batch is split over the SMs and the fp32 partials are
+ * added in a fixed order (deterministic).  x_nhwc (B, Hin, Win, 256) bf16, dy_nhwc (B, 2 Hin, 2 Win, 256) bf16 = dy_raw_nhwc of
+ * ihpr_deconv_bn_relu_train_bwd.  2 launches.  `workspace`: ihpr_deconv_wgrad_workspace_bytes bytes (64 MiB), 256-byte aligned. */
+size_t ihpr_deconv_wgrad_workspace_bytes(int Cin, int Cout);
+int ihpr_deconv_wgrad(const void *x_nhwc, const void *dy_nhwc, int B, int Cin, int Cout, int Hin, int Win,
+                      float *dweight, void *workspace, size_t workspace_bytes, void *stream);
 
 /* One reference training step of the path with HOST buffers (what a CPU caller of
  * JointLocationLoss + backward, main/train.py:67-71, holds): copies heat to the device in

@@ -42,6 +42,8 @@ SIGNATURES = {
     "ihpr_deconv_train_workspace_bytes": (c_size_t, [c_int] * 2),
     "ihpr_deconv_bn_relu_train_fwd": (c_int, [c_void_p] * 6 + [c_float, c_float] + [c_int] * 5 + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "ihpr_deconv_bn_relu_train_bwd": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 5 + [c_size_t, c_void_p]),
+    "ihpr_deconv_wgrad_workspace_bytes": (c_size_t, [c_int] * 2),
+    "ihpr_deconv_wgrad": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "ihpr_integral_l1_fwd_bwd_host": (c_int, [c_void_p, c_int] + [c_int] * 5 + [c_void_p] * 3 + [c_float] + [c_void_p] * 3 + [c_int, c_int]),
     "ihpr_host_release": (c_int, [c_int]),
     "ihpr_set_variant": (c_int, [c_int]),

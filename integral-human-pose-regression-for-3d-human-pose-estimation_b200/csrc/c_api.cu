@@ -701,6 +701,36 @@ int ihpr_deconv_bn_relu_train_bwd(const void* dout_nhwc, const void* y_raw_nhwc,
     return IHPR_OK;
 }
 
+size_t ihpr_deconv_wgrad_workspace_bytes(int Cin, int Cout) {
+    if (Cin != 256 || Cout != 256) return 0;
+    return ihpr::deconv_wgrad_workspace_bytes();
+}
+
+int ihpr_deconv_wgrad(const void* x_nhwc, const void* dy_nhwc, int B, int Cin, int Cout, int Hin, int Win, float* dweight, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!x_nhwc || !dy_nhwc || !dweight || !workspace) return fail(IHPR_EINVAL, "null argument");
+    int rc = deconv_train_check(B, Cin, Cout, Hin, Win);
+    if (rc) return rc;
+    if (((uintptr_t)x_nhwc | (uintptr_t)dy_nhwc | (uintptr_t)dweight) & 15) return fail(IHPR_EINVAL, "x / dy / dweight must be 16-byte aligned");
+    if ((uintptr_t)workspace & 255) return fail(IHPR_EINVAL, "workspace must be 256-byte aligned");
+    const size_t need = ihpr::deconv_wgrad_workspace_bytes();
+    if (workspace_bytes < need) return fail(IHPR_EINVAL, "workspace is %zu bytes, need %zu", workspace_bytes, need);
+    int num_sms = 0;
+    rc = check_device(x_nhwc, &num_sms);
+    if (rc) return rc;
+    int launches = 0;
+    // variants 21 / 22 / 24: clusters of 1 / 2 / 4 CTAs sharing the gradient tiles by TMA multicast, 64-pixel stages; 31 / 32 / 34: the same with
+    // 32-pixel stages (0: the default, see launch_deconv_wgrad)
+    const int v = g_variant;
+    const int cluster = v == 21 ? 1 : v == 22 ? 2 : v == 24 ? 4 : v == 31 ? 11 : v == 32 ? 12 : v == 34 ? 14 : 0;
+    const char* err = ihpr::launch_deconv_wgrad(x_nhwc, dy_nhwc, B, Hin, Win, dweight, workspace, num_sms, cluster, &launches, static_cast<cudaStream_t>(stream));
+    if (err) return fail(IHPR_ECUDA, "%s", err);
+    g_launches = launches;
+    IHPR_CUDA(cudaGetLastError());
+    return IHPR_OK;
+}
+
 int ihpr_integral_l1_fwd_bwd_host(const void* heat_host, int dtype, int B, int J, int D, int H, int W, const float* gt_host, const float* vis_host,
                                   const float* have_depth_host, float grad_out, float* loss_host, float* coords_host, void* grad_heat_host,
                                   int device, int slices) {

@@ -407,6 +407,9 @@ const char* launch_deconv_train_fwd(const void* x_nhwc, const void* wp_fwd, int 
                                     int* stat_rows, int num_sms, int* launches, cudaStream_t s);
 const char* launch_deconv_dgrad(const void* dy_nhwc, const void* wp_dgrad, int B, int Cin, int Cout, int Hin, int Win, void* dx_nhwc, int num_sms, int* launches,
                                 cudaStream_t s);
+size_t deconv_wgrad_workspace_bytes();
+const char* launch_deconv_wgrad(const void* x_nhwc, const void* dy_nhwc, int B, int Hin, int Win, float* dw, void* workspace, int num_sms, int cluster,
+                                int* launches, cudaStream_t s);
 int bn_bwd_rows(int num_sms);
 void launch_bn_stat_finalize(const float* part, int rows, size_t n_per_channel, const float* gamma, const float* beta, float eps, float momentum,
                              float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift, int* launches, cudaStream_t s);

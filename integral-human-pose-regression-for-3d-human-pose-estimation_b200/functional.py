@@ -453,7 +453,7 @@ class _DeconvBnReluTrain(torch.autograd.Function):
     """One deconv block of HeadNet in training (main/model.py:22-38): ConvTranspose2d(256, 256, k4, s2, p1, bias=False) + BatchNorm2d with
     batch statistics + ReLU.  Forward: the K9 GEMM in its training mode (raw output + per-channel sums from the epilogue), a finalize launch,
     one normalise + ReLU pass.  Backward: BatchNorm + ReLU backward in two streaming passes (K10), the input gradient as one tensor-core GEMM
-    (K9, mode kDgrad); the weight gradient is a library GEMM for now (aten convolution_backward on the bf16 operands).
+    (K9, mode kDgrad), the weight gradient as 16 more (K11: contraction over the pixels, MN-major operands) -- no library GEMM.
     Saved for backward: the bf16 input, the bf16 raw convolution output and 4 x 256 floats."""
 
     @staticmethod
@@ -485,6 +485,7 @@ class _DeconvBnReluTrain(torch.autograd.Function):
             torch.autograd.graph.increment_version(running_var)
         ctx.save_for_backward(xb, wb, y_raw, saved)
         ctx.meta = (x.dtype, weight.dtype, gamma.dtype, beta.dtype)
+        ctx.variant = L.ihpr_get_variant()          # per calling thread: autograd runs backward on another one
         return out
 
     @staticmethod
@@ -496,6 +497,7 @@ class _DeconvBnReluTrain(torch.autograd.Function):
         dev = xb.device
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         L = lib()
+        L.ihpr_set_variant(ctx.variant)
         go = _nhwc_bf16(grad_out)
         dy = torch.empty_like(y_raw)
         dgb = torch.empty((2, Cout), dtype=torch.float32, device=dev)
@@ -507,9 +509,17 @@ class _DeconvBnReluTrain(torch.autograd.Function):
                                                   dgb[0].data_ptr(), dgb[1].data_ptr(), dx.data_ptr() if dx is not None else None,
                                                   ws.data_ptr(), nbytes, stream))
         dw = None
-        if need_w:
-            # weight gradient: x^T . dy per tap -- the one GEMM of this block still left to the library
+        if need_w and os.environ.get("IHPR_DECONV_WGRAD", "k11") == "library":
+            # comparison arm: the weight gradient from the library (cuDNN wgrad through aten)
             dw = torch.ops.aten.convolution_backward(dy, xb, wb, None, [2, 2], [1, 1], [1, 1], True, [0, 0], 1, [False, True, False])[1].to(w_dtype)
+        elif need_w:
+            # K11: x^T . dy per tap on the tensor cores, fp32 partials added in a fixed order
+            dw = torch.empty((Cin, Cout, 4, 4), dtype=torch.float32, device=dev)
+            nb2 = L.ihpr_deconv_wgrad_workspace_bytes(Cin, Cout)
+            ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
+            with _on_device(dev) as stream:
+                check(L.ihpr_deconv_wgrad(xb.data_ptr(), dy.data_ptr(), B, Cin, Cout, H, W, dw.data_ptr(), ws2.data_ptr(), nb2, stream))
+            dw = dw.to(w_dtype)
         return (dx.to(x_dtype) if dx is not None else None, dw, dgb[0].to(g_dtype) if ctx.needs_input_grad[2] else None,
                 dgb[1].to(b_dtype) if ctx.needs_input_grad[3] else None, None, None, None, None)
 

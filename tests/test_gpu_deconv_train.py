@@ -186,6 +186,73 @@ def test_input_gradient_impulses_place_every_tap_and_do_not_cross_samples(dev):
         assert int((dx[b] != 0).sum()) > 0
 
 
+def _wgrad(x, dy):
+    """ihpr_deconv_wgrad through the C-ABI: x (B, 256, H, W), dy (B, 256, 2H, 2W) bf16 -> (256, 256, 4, 4) fp32"""
+    from ihpr_b200._lib import lib, check
+    L = lib()
+    dev = x.device
+    B, _, H, W = x.shape
+    xb = x.contiguous(memory_format=torch.channels_last)
+    dyb = dy.contiguous(memory_format=torch.channels_last)
+    dw = torch.empty((256, 256, 4, 4), dtype=torch.float32, device=dev)
+    n = L.ihpr_deconv_wgrad_workspace_bytes(256, 256)
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(L.ihpr_deconv_wgrad(xb.data_ptr(), dyb.data_ptr(), B, 256, 256, H, W, dw.data_ptr(), ws.data_ptr(), n, torch.cuda.current_stream(dev).cuda_stream))
+    assert L.ihpr_last_launch_count() == 2
+    return dw
+
+
+@pytest.fixture(autouse=True)
+def _reset_variant():
+    yield
+    import ihpr_b200
+    ihpr_b200.set_variant(0)
+
+
+# 0: the default; 21 / 22 / 24: clusters of 1 / 2 / 4 CTAs (TMA multicast of the gradient tiles), 64-pixel stages; 31 / 32 / 34: 32-pixel stages
+@pytest.mark.parametrize("variant", [0, 21, 22, 24, 31, 32, 34])
+@pytest.mark.parametrize("case", CASES + [(1, 8, 32)])      # (1, 8, 32): 4 tiles per (phase, tap) -- fewer tiles than SMs / 16, the split shrinks
+def test_weight_gradient_vs_fp64(case, variant, dev):
+    """K11: dW of the transposed convolution against torch's fp64 autograd on the same bf16 operands.  The kernel accumulates bf16 products in
+    fp32 (one 64-pixel tile after the other, then the batch splits in index order) and never rounds to bf16: 1e-4 of the largest entry."""
+    B, Hin, Win = case
+    g = torch.Generator().manual_seed(B * 31 + Hin)
+    x = torch.randn(B, 256, Hin, Win, generator=g).to(torch.bfloat16).to(dev)
+    dy = torch.randn(B, 256, 2 * Hin, 2 * Win, generator=g).to(torch.bfloat16).to(dev)
+    import ihpr_b200
+    ihpr_b200.set_variant(variant)
+    dw = _wgrad(x, dy)
+    dw2 = _wgrad(x, dy)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)                  # fixed reduction order
+    w0 = torch.zeros(256, 256, 4, 4, dtype=torch.float64, device=dev, requires_grad=True)
+    (F.conv_transpose2d(x.double(), w0, stride=2, padding=1) * dy.double()).sum().backward()
+    err = float((dw.double() - w0.grad).abs().max() / w0.grad.abs().max())
+    assert err <= 1e-4, err
+
+
+def test_weight_gradient_impulses_place_every_tap(dev):
+    """x = a single 1 at (b, ci, iy, ix), dy = a single 1 at (b, co, oy, ox): dW[ci, co, ky, kx] = 1 exactly where oy = 2 iy + ky - 1 and
+    ox = 2 ix + kx - 1, 0 everywhere else -- every tap, both parities, the borders, and pairs in different samples (which must give 0)."""
+    B, H, W = 2, 32, 32
+    spots = [((0, 7, 0, 0), (0, 9, 0, 0)), ((0, 7, 0, 0), (0, 9, 1, 2)), ((1, 100, 31, 31), (1, 3, 63, 63)), ((1, 100, 31, 31), (1, 3, 61, 62)),
+             ((0, 255, 16, 5), (0, 0, 31, 9)), ((0, 255, 16, 5), (0, 0, 34, 12)), ((1, 64, 0, 31), (1, 200, 2, 63)),
+             ((0, 1, 31, 0), (1, 2, 62, 0)),          # different samples: no contribution at all
+             ((0, 1, 5, 5), (0, 2, 20, 20))]          # too far apart: no tap connects them
+    for (b, ci, iy, ix), (b2, co, oy, ox) in spots:
+        x = torch.zeros((B, 256, H, W), dtype=torch.bfloat16, device=dev)
+        dy = torch.zeros((B, 256, 2 * H, 2 * W), dtype=torch.bfloat16, device=dev)
+        x[b, ci, iy, ix] = 1.0
+        dy[b2, co, oy, ox] = 1.0
+        dw = _wgrad(x, dy)
+        want = torch.zeros_like(dw)
+        ky, kx = oy + 1 - 2 * iy, ox + 1 - 2 * ix
+        if b == b2 and 0 <= ky < 4 and 0 <= kx < 4:
+            want[ci, co, ky, kx] = 1.0
+        torch.cuda.synchronize()
+        assert torch.equal(dw, want), ((b, ci, iy, ix), (b2, co, oy, ox), dw.nonzero().tolist()[:8])
+
+
 def test_autograd_block_vs_torch_fp64_autograd(dev):
     """deconv_bn_relu_train as a differentiable function against torch's fp64 autograd of the same block (bf16-rounded operands).
     Element-wise bounds do not survive ReLU-mask flips of values that round across zero, so gradients are compared in the L2 norm."""

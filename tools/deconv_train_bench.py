@@ -12,9 +12,11 @@ ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--H", type=int, default=32)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--variant", type=int, default=0, help="K11: 21 / 22 / 24 = clusters of 1 / 2 / 4 CTAs, 64-pixel stages; 31 / 32 / 34 = 32-pixel stages")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True
+ihpr_b200.set_variant(a.variant)
 B, H = a.B, a.H
 x = torch.randn(B, 256, H, H, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
 deconv = torch.nn.ConvTranspose2d(256, 256, 4, 2, 1, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
@@ -64,7 +66,7 @@ gx_f, gw_f = x.grad.float().clone(), deconv.weight.grad.float().clone()
 step(stock)()
 gx_s, gw_s = x.grad.float(), deconv.weight.grad.float()
 flop = 2.0 * B * (2 * H) ** 2 * 256 * 1024
-print(json.dumps({"B": B, "H": H, "fused_fwd_us": round(t_f, 1), "stock_fwd_us": round(t_s, 1), "fused_fwd_bwd_us": round(t_fb, 1), "stock_fwd_bwd_us": round(t_sb, 1),
+print(json.dumps({"B": B, "H": H, "wgrad": os.environ.get("IHPR_DECONV_WGRAD", "k11"), "variant": a.variant, "fused_fwd_us": round(t_f, 1), "stock_fwd_us": round(t_s, 1), "fused_fwd_bwd_us": round(t_fb, 1), "stock_fwd_bwd_us": round(t_sb, 1),
                   "fwd_speedup": round(t_s / t_f, 2), "fwd_bwd_speedup": round(t_sb / t_fb, 2), "gemm_GFLOP": round(flop / 1e9, 1),
                   "dx_rel_diff_vs_stock": round(float((gx_f - gx_s).norm() / gx_s.norm()), 5),
                   "dw_rel_diff_vs_stock": round(float((gw_f - gw_s).norm() / gw_s.norm()), 5)}))
