@@ -184,3 +184,42 @@ def test_head_features_keeps_the_stock_stack_where_k9_does_not_apply(built_lib):
     assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 128, 32, 32, 256, None) < 0         # C_out must be 256
     assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 256, 32, 8, 256, None) < 0          # width 8
     assert L.ihpr_deconv_bn_relu(256, 256, 1, 256, 256, 8, 16, 256, None) < 0          # width 16 needs a height that is a multiple of 16
+
+
+def test_training_deconv_block_falls_back_on_cpu_and_its_entries_check_arguments(built_lib):
+    """HeadNet.features(x, fused_training=True) is the stock module stack wherever the training kernels (K9 kTrain / kDgrad, K10, K11: CUDA,
+    256 -> 256 channels, 16- / 32-wide map) do not apply -- on the CPU always, with identical running statistics; the training entries of the
+    C-ABI report bad arguments before any CUDA call."""
+    import copy
+    from ihpr_b200._lib import lib
+    from ihpr_b200.model import get_pose_net
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=4)
+    torch.manual_seed(0)
+    net = get_pose_net(cfg, True, 3, fused_head=True)
+    assert net.fused_deconv and not get_pose_net(cfg, True, 3, fused_head=True, fused_deconv=False).fused_deconv
+    assert not get_pose_net(cfg, True, 3).fused_deconv                  # only where the fused head is used
+    ref = copy.deepcopy(net)
+    x = torch.randn(2, 512, 8, 8)
+    net.train()
+    ref.train()
+    y = net.head.features(x, fused_training=True)
+    assert torch.equal(y, ref.head.deconv_layers(x)) and y.requires_grad
+    for (n, a), (_, b) in zip(net.head.named_buffers(), ref.head.named_buffers()):
+        assert torch.equal(a, b), n
+    L = lib()
+    n = L.ihpr_deconv_train_workspace_bytes(256, 256)
+    assert n >= 2 * 16 * 256 * 256 * 2 and L.ihpr_deconv_train_workspace_bytes(0, 256) == 0
+    assert L.ihpr_deconv_wgrad_workspace_bytes(256, 256) >= 9 * 16 * 256 * 256 * 4 and L.ihpr_deconv_wgrad_workspace_bytes(128, 256) == 0
+    p = 256         # any non-null, aligned value: the checks below fail before a pointer is looked at
+    fwd = lambda Cin=256, Cout=256, H=32, W=32, nb=n, rm=None, rv=None: L.ihpr_deconv_bn_relu_train_fwd(  # noqa: E731
+        p, p, p, p, rm, rv, 0.1, 1e-5, 1, Cin, Cout, H, W, p, p, p, p, nb, None)
+    assert L.ihpr_deconv_bn_relu_train_fwd(None, p, p, p, None, None, 0.1, 1e-5, 1, 256, 256, 32, 32, p, p, p, p, n, None) < 0
+    assert fwd(Cin=128) < 0 and b"C_in == C_out == 256" in L.ihpr_last_error()
+    assert fwd(Cout=128) < 0 and fwd(W=8) < 0 and fwd(H=12, W=16) < 0
+    assert fwd(rm=p) < 0 and b"come together" in L.ihpr_last_error()
+    assert fwd(nb=n - 1) < 0 and b"workspace" in L.ihpr_last_error()
+    assert L.ihpr_deconv_bn_relu_train_bwd(p, p, None, p, 1, 256, 256, 32, 32, p, p, p, p, p, n, None) < 0        # dx without the weight
+    assert L.ihpr_deconv_bn_relu_train_bwd(p, p, p, p, 1, 256, 256, 32, 24, p, p, p, None, p, n, None) < 0
+    assert L.ihpr_deconv_wgrad(p, p, 1, 256, 256, 32, 32, None, p, 1 << 30, None) < 0
+    assert L.ihpr_deconv_wgrad(p, p, 1, 256, 256, 32, 32, p, p, 1024, None) < 0 and b"workspace" in L.ihpr_last_error()
+    assert L.ihpr_deconv_wgrad(p, p, 0, 256, 256, 32, 32, p, p, 1 << 30, None) < 0
