@@ -263,16 +263,70 @@ __device__ __forceinline__ void fold_w2(Acc& a, uint64_t& w2) {
     w2 = 0;             // two +0.0f
 }
 
+// the arithmetic of consume_chunk_fast_pk on U vectors that are already in registers (yf / zf: the row / slice of the thread's first vector,
+// advanced here by rsf rows per vector)
+template <typename T, int U>
+__device__ __forceinline__ void consume_vectors_pk(Acc& a, uint64_t& w2, const uint4 (&raw)[U], float& yf, float& zf, float rsf, float hf) {
+    constexpr int QPV = Elem<T>::QPV;
+    constexpr int NP = 2 * QPV;             // fp32 pairs per 16-byte vector
+    const uint64_t l2e2 = pk2f(kLog2e, kLog2e);
+    float cmax;
+    if (sizeof(T) == 2) {               // maximum on the packed bf16 words: 4 instructions per vector instead of 8
+        uint32_t m = bmax2(bmax2(raw[0].x, raw[0].y), bmax2(raw[0].z, raw[0].w));
+#pragma unroll
+        for (int u = 1; u < U; ++u) m = bmax2(m, bmax2(bmax2(raw[u].x, raw[u].y), bmax2(raw[u].z, raw[u].w)));
+        cmax = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+    } else {
+        cmax = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            cmax = fmaxf(cmax, fmaxf(fmaxf(__uint_as_float(raw[u].x), __uint_as_float(raw[u].y)),
+                                     fmaxf(__uint_as_float(raw[u].z), __uint_as_float(raw[u].w))));
+    }
+    a.mx = fmaxf(a.mx, cmax);
+    if (cmax > a.lim) {
+        fold_w2(a, w2);
+        acc_raise(a, cmax);
+    }
+    const uint64_t nc2 = pk2f(-a.c, -a.c);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint64_t pp[NP];
+        if (sizeof(T) == 2) {           // bf16 -> fp32 is a shift / a mask, written straight into the halves of a pair
+            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pp[i % NP] = pk2w(w[i] << 16, w[i] & 0xffff0000u);
+        } else {
+            pp[0] = pk2w(raw[u].x, raw[u].y);
+            pp[1] = pk2w(raw[u].z, raw[u].w);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            float t0, t1;
+            up2f(ffma2p(pp[i], l2e2, nc2), t0, t1);
+            pp[i] = pk2f(ex2(t0), ex2(t1));
+            w2 = ffma2p(pp[i], pk2f((float)(2 * i), (float)(2 * i + 1)), w2);      // within-vector x moment, even / odd halves
+        }
+        uint64_t s2 = fadd2p(pp[0], pp[1]);
+        if (NP == 4) s2 = fadd2p(s2, fadd2p(pp[2], pp[3]));
+        float s_lo, s_hi;
+        up2f(s2, s_lo, s_hi);
+        const float sv = s_lo + s_hi;
+        a.l += sv;
+        a.sy = fmaf(sv, yf, a.sy);
+        a.sz = fmaf(sv, zf, a.sz);
+        yf += rsf;
+        if (yf >= hf) { yf -= hf; zf += 1.f; }
+    }
+}
+
 template <typename T, int U, int NC, int VPC, bool FULL, typename Loader>
 __device__ __forceinline__ void consume_chunk_fast_pk(Acc& a, uint64_t& w2, const Geometry& g, uint32_t n_vec, uint32_t vbase, int tid, float rsf,
                                                       float hf, Loader load) {
-    constexpr int QPV = Elem<T>::QPV;
-    constexpr int NP = 2 * QPV;             // fp32 pairs per 16-byte vector
     const uint32_t zy0 = fdiv(vbase + tid, g.divFv);
     const uint32_t z0 = fdiv(zy0, g.divH);
     float yf = u2f(zy0 - z0 * g.divH.d), zf = u2f(z0);
     const uint32_t nv = FULL ? (uint32_t)VPC : n_vec;
-    const uint64_t l2e2 = pk2f(kLog2e, kLog2e);
 #pragma unroll
     for (uint32_t base = 0; base < nv; base += NC * U) {
         uint4 raw[U];
@@ -283,54 +337,7 @@ __device__ __forceinline__ void consume_chunk_fast_pk(Acc& a, uint64_t& w2, cons
             else raw[u] = (sizeof(T) == 4 ? make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u)
                                           : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u));
         }
-        float cmax;
-        if (sizeof(T) == 2) {               // maximum on the packed bf16 words: 4 instructions per vector instead of 8
-            uint32_t m = bmax2(bmax2(raw[0].x, raw[0].y), bmax2(raw[0].z, raw[0].w));
-#pragma unroll
-            for (int u = 1; u < U; ++u) m = bmax2(m, bmax2(bmax2(raw[u].x, raw[u].y), bmax2(raw[u].z, raw[u].w)));
-            cmax = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
-        } else {
-            cmax = -INFINITY;
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                cmax = fmaxf(cmax, fmaxf(fmaxf(__uint_as_float(raw[u].x), __uint_as_float(raw[u].y)),
-                                         fmaxf(__uint_as_float(raw[u].z), __uint_as_float(raw[u].w))));
-        }
-        a.mx = fmaxf(a.mx, cmax);
-        if (cmax > a.lim) {
-            fold_w2(a, w2);
-            acc_raise(a, cmax);
-        }
-        const uint64_t nc2 = pk2f(-a.c, -a.c);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            uint64_t pp[NP];
-            if (sizeof(T) == 2) {           // bf16 -> fp32 is a shift / a mask, written straight into the halves of a pair
-                const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) pp[i % NP] = pk2w(w[i] << 16, w[i] & 0xffff0000u);
-            } else {
-                pp[0] = pk2w(raw[u].x, raw[u].y);
-                pp[1] = pk2w(raw[u].z, raw[u].w);
-            }
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                float t0, t1;
-                up2f(ffma2p(pp[i], l2e2, nc2), t0, t1);
-                pp[i] = pk2f(ex2(t0), ex2(t1));
-                w2 = ffma2p(pp[i], pk2f((float)(2 * i), (float)(2 * i + 1)), w2);      // within-vector x moment, even / odd halves
-            }
-            uint64_t s2 = fadd2p(pp[0], pp[1]);
-            if (NP == 4) s2 = fadd2p(s2, fadd2p(pp[2], pp[3]));
-            float s_lo, s_hi;
-            up2f(s2, s_lo, s_hi);
-            const float sv = s_lo + s_hi;
-            a.l += sv;
-            a.sy = fmaf(sv, yf, a.sy);
-            a.sz = fmaf(sv, zf, a.sz);
-            yf += rsf;
-            if (yf >= hf) { yf -= hf; zf += 1.f; }
-        }
+        consume_vectors_pk<T, U>(a, w2, raw, yf, zf, rsf, hf);
     }
 }
 

@@ -221,6 +221,27 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster_kernel(const FwdParams p) {
         Acc a;
         a.reset();
         uint64_t w2 = 0;
+        if (fast && g.N % g.CE == 0) {
+            // every chunk is full: the loads of chunk k + 1 are issued before chunk k is consumed (a CTA streams only 4 ... 16 chunks, so
+            // an un-pipelined loop pays the L2 / DRAM latency once per chunk: ~0.7 us each, most of the kernel at B = 1)
+            auto fetch = [&](uint32_t k, uint4 (&dst)[U]) {
+                const uint8_t* cp = src + ((size_t)r * g.N + (size_t)k * g.CE) * sizeof(T) + (size_t)tid * 16;
+#pragma unroll
+                for (int u = 0; u < U; ++u) dst[u] = ld_stream16(cp + (size_t)u * NT * 16);
+            };
+            uint4 nxt[U];
+            if (k0 < k1) fetch(k0, nxt);
+            for (uint32_t k = k0; k < k1; ++k) {
+                uint4 cur[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+                if (k + 1 < k1) fetch(k + 1, nxt);
+                const uint32_t zy0 = fdiv(k * VPC + tid, g.divFv);
+                const uint32_t z0 = fdiv(zy0, g.divH);
+                float yf = u2f(zy0 - z0 * g.divH.d), zf = u2f(z0);
+                consume_vectors_pk<T, U>(a, w2, cur, yf, zf, rsf, hf);
+            }
+        } else
         for (uint32_t k = k0; k < k1; ++k) {
             const uint32_t e0 = k * g.CE;
             const uint32_t n_vec = min(g.CE, g.N - e0) / (4 * QPV);
@@ -366,8 +387,13 @@ static int cluster_capacity(int CS) {
 // TMA ring); beyond that every SM streams plenty in the persistent kernels and their tail is amortised.
 int fwd_cluster_size(const Geometry& g, int dtype) {
     if (getenv("IHPR_NO_K1C")) return 0;
-    if (g.nch >= 4 && g.R <= (dtype == 0 ? cluster_capacity<float>(4) : cluster_capacity<__nv_bfloat16>(4))) return 4;
-    if (dtype != 0 && g.nch >= 2 && g.R <= cluster_capacity<__nv_bfloat16>(2)) return 2;
+    auto cap = [&](int cs) { return dtype == 0 ? cluster_capacity<float>(cs) : cluster_capacity<__nv_bfloat16>(cs); };
+    if (const char* e = getenv("IHPR_K1C_CS")) {          // tuning experiments: force a cluster size (0 = the ring kernel)
+        const int cs = atoi(e);
+        return ((cs == 2 || cs == 4 || cs == 8) && g.nch >= (uint32_t)cs && g.R <= cap(cs)) ? cs : 0;
+    }
+    if (g.nch >= 4 && g.R <= cap(4)) return 4;
+    if (dtype != 0 && g.nch >= 2 && g.R <= cap(2)) return 2;
     return 0;
 }
 

@@ -48,9 +48,10 @@ class HeadNet(nn.Module):
             h, w = x.shape[2], x.shape[3]
             ok = (isinstance(conv, nn.ConvTranspose2d) and isinstance(bn, nn.BatchNorm2d) and conv.out_channels == 256 and conv.in_channels % 64 == 0
                   and conv.in_channels <= 1024 and w in (16, 32) and h % (256 // w) == 0 and bn.affine)
-            if ok and infer and bn.track_running_stats:
+            if ok and infer and bn.track_running_stats and not bn.training:
                 x = deconv_bn_relu(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-            elif ok and train and conv.in_channels == 256 and x.shape[0] > 0 and bn.momentum is not None:
+            elif ok and train and bn.training and conv.in_channels == 256 and x.shape[0] > 0 and bn.momentum is not None:
+                # (a BatchNorm that is frozen -- .eval() inside a training head -- uses running statistics WITH gradients: the stock modules)
                 x = deconv_bn_relu_train(x, conv.weight, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
                                          bn.running_var if bn.track_running_stats else None, bn.momentum, bn.eps)
                 if bn.track_running_stats and bn.num_batches_tracked is not None:

@@ -360,3 +360,22 @@ def test_fused_training_step_matches_the_stock_deconv_stack(dev):
     for name in ("head.deconv_layers.7.running_mean", "head.deconv_layers.7.running_var", "head.deconv_layers.4.running_var"):
         np.testing.assert_allclose(ba[name].cpu().numpy(), bb[name].cpu().numpy(), rtol=2e-2, atol=2e-3)
     assert int(ba["head.deconv_layers.7.num_batches_tracked"]) == 1
+
+
+def test_frozen_batchnorm_in_a_training_head_keeps_the_stock_modules(dev):
+    """A BatchNorm2d switched to eval() inside a training head (frozen statistics, what the two-rank equality test does) must normalise with
+    its RUNNING statistics and still propagate gradients: HeadNet.features leaves such a block to the stock modules."""
+    import types
+    import ihpr_b200.model as M
+    cfg = types.SimpleNamespace(resnet_type=18, depth_dim=8)
+    torch.manual_seed(0)
+    net = M.get_pose_net(cfg, True, 3, fused_head=True).to(dev)
+    net.train()
+    for m in net.head.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+            m.running_mean.normal_(0, 0.1)
+    x = torch.randn(2, 512, 8, 8, device=dev)
+    a = net.head.features(x, fused_training=True)
+    b = net.head.deconv_layers(x)
+    assert torch.equal(a, b) and a.requires_grad
