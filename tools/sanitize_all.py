@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/sanitize_all.py -- one small invocation of every kernel family of the library (K1/K2 ring, direct and scalar paths, K1c, K5, K5c with
-clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6, K9) with finiteness checks: a quick all-kernel smoke on a B200, and the
+clusters of 2 / 8 / 16, K3 / K4w / K4x single-SM and SM-pair, K6, K9 at inference and in training with K10 / K11) with finiteness checks: a quick all-kernel smoke on a B200, and the
 driver to put under `compute-sanitizer --tool memcheck|racecheck|synccheck` where the pool allows it (round 1's pool does not)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -65,6 +65,18 @@ for Bq in (1, 10):
                                       torch.ones(256, device=dev), 1e-5)
     torch.cuda.synchronize()
     assert torch.isfinite(yq.float()).all().item()
+# K9 kTrain + K10 + K9 kDgrad + K11: the deconv block in training, forward and backward (32- and 16-wide maps; K11 also on clusters of 2 / 4)
+for (Bq, Hq, vq) in ((2, 32, 0), (3, 16, 0), (2, 32, 22), (2, 32, 24), (2, 32, 31)):
+    ihpr_b200.set_variant(vq)
+    xq = torch.randn(Bq, 256, Hq, Hq, generator=g).to(dev).requires_grad_(True)
+    wq = (torch.randn(256, 256, 4, 4, generator=g) * 0.05).to(dev).requires_grad_(True)
+    gq, bq = torch.ones(256, device=dev, requires_grad=True), torch.zeros(256, device=dev, requires_grad=True)
+    rm, rv = torch.zeros(256, device=dev), torch.ones(256, device=dev)
+    yq = ihpr_b200.deconv_bn_relu_train(xq, wq, gq, bq, rm, rv, 0.1, 1e-5)
+    yq.float().square().sum().backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(t.float()).all().item() for t in (yq, xq.grad, wq.grad, gq.grad, bq.grad, rm, rv))
+ihpr_b200.set_variant(0)
 # K6: test-time post-processing
 B, J = 3, 18
 coords = torch.rand(B, J, 3, device=dev) * 64
