@@ -295,7 +295,9 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     p.xc_chunks = p.xc_lag = 0;
     p.loss_scale = scale;
 #ifdef IHPR_TIMING_EXPERIMENTS
-    p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") != nullptr;      // wrong results: only in builds made for timing experiments
+    // builds made for timing experiments only: bit 0 = skip the cross-CTA trade (WRONG results), bit 1 = pass 1 without the L2 evict_last hint,
+    // bit 2 = pass 2 without the evict_first hint
+    p.debug_no_exchange = getenv("IHPR_DEBUG_NOXCHG") ? atoi(getenv("IHPR_DEBUG_NOXCHG")) : 0;
 #else
     p.debug_no_exchange = 0;
 #endif

@@ -79,7 +79,15 @@ __global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(c
     if (warp == 0) {
         // ================= producer =================
         if (lane == 0) {
-            const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+            uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+#ifdef IHPR_TIMING_EXPERIMENTS
+            if (p.debug_no_exchange & 6) {
+                uint64_t pol_normal;
+                asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+                if (p.debug_no_exchange & 2) pol_keep = pol_normal;
+                if (p.debug_no_exchange & 4) pol_drop = pol_normal;
+            }
+#endif
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.f.heat);
             uint32_t it = 0;
             auto issue = [&](uint32_t u, int pass) {
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(c
             t.reset();
             if (lane < NCW) t = partial_from_smem(pbuf[b * NCW + lane]);
             t = acc_warp_merge(t);
-            if (S > 1 && !p.debug_no_exchange) {
+            if (S > 1 && !(p.debug_no_exchange & 1)) {
                 uint2* row = p.xslots + (size_t)r * (kMaxSplit * 8);
                 if (lane < 6) {
                     const float w = lane == 0 ? t.m : lane == 1 ? t.l : lane == 2 ? t.sx : lane == 3 ? t.sy : lane == 4 ? t.sz : t.mx;
@@ -129,22 +137,19 @@ __global__ void __launch_bounds__((NCW + DEPTH + 2) * 32, 1) fused_ring_kernel(c
                 }
                 t.reset();
                 if (lane < S) {
-                    // poll ONE pair per partner (keeps the polling traffic of 4 x 144 exchanger warps small), then
-                    // fetch the other five and re-check their tags: stores of different lanes are not ordered
+                    // all six pairs of the partner's slot (one 64-byte line) are polled together: every poll is a trip through memory
+                    // queues that the TMA rings keep ~4 us deep (144 CTAs x 192 KiB in flight at 6.5 TB/s), so "poll one pair, then fetch
+                    // the other five" cost a second such trip per exchange; stores of different lanes are not ordered, hence a tag per pair
                     const uint2* slot = row + lane * 8;
                     uint2 w[6];
                     for (;;) {
-                        w[0] = ld_pair(slot);
-                        if (w[0].y == tag) break;
-                        __nanosleep(100);
-                    }
-                    for (;;) {
 #pragma unroll
-                        for (int i = 1; i < 6; ++i) w[i] = ld_pair(slot + i);
+                        for (int i = 0; i < 6; ++i) w[i] = ld_pair(slot + i);
                         bool ok = true;
 #pragma unroll
-                        for (int i = 1; i < 6; ++i) ok = ok && (w[i].y == tag);
+                        for (int i = 0; i < 6; ++i) ok = ok && (w[i].y == tag);
                         if (ok) break;
+                        __nanosleep(64);
                     }
                     t.m = __uint_as_float(w[0].x); t.l = __uint_as_float(w[1].x); t.sx = __uint_as_float(w[2].x);
                     t.sy = __uint_as_float(w[3].x); t.sz = __uint_as_float(w[4].x); t.mx = __uint_as_float(w[5].x);
@@ -322,9 +327,9 @@ int fused_split(const Geometry& g, int dtype) {
     return S < 1 ? 1 : S;
 }
 
-template <typename T, int DEPTH>
-static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_t s) {
-    constexpr int CB = 32768, ST = 6, NCW = 16, NB = DEPTH + 1;
+template <typename T, int DEPTH, int ST>
+static cudaError_t launch_fused_ds(const FusedParams& p, int num_sms, cudaStream_t s) {
+    constexpr int CB = 32768, NCW = 16, NB = DEPTH + 1;
     auto kern = fused_ring_kernel<T, CB, ST, NCW, DEPTH>;
     const size_t smem = (size_t)ST * CB + (2 * ST + 3 * NB) * sizeof(uint64_t) + (size_t)(NB * NCW + NB) * 8 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -344,6 +349,21 @@ static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+// ring depth: IHPR_FUSED_STAGES = 3 / 4 / 6 (tuning experiments; default 6)
+static int fused_stages() {
+    const char* e = getenv("IHPR_FUSED_STAGES");
+    const int st = e ? atoi(e) : 6;
+    return st == 3 || st == 4 ? st : 6;
+}
+template <typename T, int DEPTH>
+static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_t s) {
+    switch (fused_stages()) {
+        case 3: return launch_fused_ds<T, DEPTH, 3>(p, num_sms, s);
+        case 4: return launch_fused_ds<T, DEPTH, 4>(p, num_sms, s);
+        default: return launch_fused_ds<T, DEPTH, 6>(p, num_sms, s);
+    }
 }
 
 template <typename T>
