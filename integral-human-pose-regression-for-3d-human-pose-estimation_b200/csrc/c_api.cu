@@ -107,7 +107,10 @@ int fwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
     if (rc) return rc;
 
     const bool v = vec_ok(heat, nullptr, dtype, D, H, W);
-    const int variant = g_variant;
+    int variant = g_variant;
+    // auto: a large batch streams the forward through a ring of 3 x 64 KiB (variant 15: two consumer rounds per barrier hand-shake; bf16 B = 32
+    // 66.2 -> 60.5 us, fp32 98.9 -> 97.1 us) once there are enough 64 KiB chunks per SM for the even split not to matter (>= 256 MiB)
+    if (variant == 0 && v && (uint64_t)B * J * D * H * W * (dtype == IHPR_F32 ? 4 : 2) >= (256ull << 20)) variant = 15;
     ihpr::FwdParams p;
     p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
     p.heat = heat; p.coords = coords; p.stats = stats;
@@ -136,7 +139,9 @@ int bwd_common(const void* heat, int dtype, int B, int J, int D, int H, int W, c
     rc = check_device(heat, &num_sms);
     if (rc) return rc;
     const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
-    const int variant = g_variant;
+    int variant = g_variant;
+    // auto, bf16: the same 3 x 64 KiB ring as the forward for large batches (106.1 -> 104.4 us at B = 32); fp32 keeps launch_bwd's own rule
+    if (variant == 0 && v && dtype == IHPR_BF16 && (uint64_t)B * J * D * H * W * 2 >= (256ull << 20)) variant = 15;
     ihpr::BwdParams p;
     p.g = ihpr::make_geometry(B, J, D, H, W, dtype, v, variant);
     p.heat = heat; p.grad_heat = grad_heat; p.coords = coords; p.stats = stats;

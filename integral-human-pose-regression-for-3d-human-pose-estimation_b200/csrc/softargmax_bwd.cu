@@ -191,6 +191,8 @@ static void launch_bwd_t(const BwdParams& p, bool vec_ok, int variant, int num_s
         case 12: return launch_ring<T, 16384, 12, 16, 1>(p, num_sms, s);
         case 13: return launch_ring<T, 16384, 6, 8, 2>(p, num_sms, s);
         case 14: return launch_ring<T, 32768, 3, 16, 2>(p, num_sms, s);
+        case 15: return launch_ring<T, 65536, 3, 16, 1>(p, num_sms, s);
+        case 16: return launch_ring<T, 98304, 2, 16, 1>(p, num_sms, s);
         case 1: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
         default:
             // auto: once the volumes no longer fit L2 (>= 128 MiB) the fp32 backward streams faster with direct 128-bit loads, two

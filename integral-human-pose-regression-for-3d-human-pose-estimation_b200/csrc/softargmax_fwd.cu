@@ -317,6 +317,8 @@ static uint32_t chunk_bytes_of(bool vec_ok, int variant) {
         case 2: return 32768;       // direct: 512 threads x 4 x 16 B
         case 1: case 12: case 13: return 16384;
         case 21: return 16384;      // direct: 256 threads x 4 x 16 B
+        case 15: return 65536;      // ring of 3 x 64 KiB: two consumer rounds per barrier hand-shake
+        case 16: return 98304;      // ring of 2 x 96 KiB: three rounds per hand-shake
         default: return 32768;      // 0 (auto), 11, 14
     }
 }
@@ -411,6 +413,8 @@ static void launch_fwd_t(const FwdParams& p, bool vec_ok, int variant, int num_s
         case 12: return launch_ring<T, 16384, 12, 16, 1>(p, num_sms, s);
         case 13: return launch_ring<T, 16384, 6, 8, 2>(p, num_sms, s);
         case 14: return launch_ring<T, 32768, 3, 16, 2>(p, num_sms, s);
+        case 15: return launch_ring<T, 65536, 3, 16, 1>(p, num_sms, s);
+        case 16: return launch_ring<T, 98304, 2, 16, 1>(p, num_sms, s);
         case 1: return launch_ring<T, 16384, 12, 8, 1>(p, num_sms, s);
         default: return launch_ring<T, 32768, 6, 16, 1>(p, num_sms, s);
     }

@@ -22,7 +22,7 @@ from oracle import inputs, truth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 1, 12, 13, 14, 2, 21]
+VARIANTS = [0, 1, 12, 13, 14, 15, 16, 2, 21]
 TOL = 1e-4
 
 
