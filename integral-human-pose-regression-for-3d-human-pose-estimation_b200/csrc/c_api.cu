@@ -250,7 +250,9 @@ int ihpr_integral_l1_fwd_bwd(const void* heat, int dtype, int B, int J, int D, i
     const bool v = vec_ok(heat, grad_heat, dtype, D, H, W);
     const int variant = g_variant;
     const float scale = 1.0f / (3.0f * (float)B * (float)J);
-    ihpr::Geometry g = ihpr::make_geometry(B, J, D, H, W, dtype, v, 0);
+    // (IHPR_FUSED_CHUNK=64: K5 on 64 KiB chunks, a tuning experiment -- set IHPR_FUSED_SPLIT to a divisor of the chunk count with it)
+    static const bool chunk64 = [] { const char* e = getenv("IHPR_FUSED_CHUNK"); return e && atoi(e) == 64; }();
+    ihpr::Geometry g = ihpr::make_geometry(B, J, D, H, W, dtype, v, chunk64 ? 15 : 0);
     int num_sms = 0;
     rc = check_device(heat, &num_sms);
     if (rc) return rc;

@@ -327,9 +327,9 @@ int fused_split(const Geometry& g, int dtype) {
     return S < 1 ? 1 : S;
 }
 
-template <typename T, int DEPTH, int ST>
+template <typename T, int DEPTH, int ST, int CB = 32768>
 static cudaError_t launch_fused_ds(const FusedParams& p, int num_sms, cudaStream_t s) {
-    constexpr int CB = 32768, NCW = 16, NB = DEPTH + 1;
+    constexpr int NCW = 16, NB = DEPTH + 1;
     auto kern = fused_ring_kernel<T, CB, ST, NCW, DEPTH>;
     const size_t smem = (size_t)ST * CB + (2 * ST + 3 * NB) * sizeof(uint64_t) + (size_t)(NB * NCW + NB) * 8 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -359,6 +359,7 @@ static int fused_stages() {
 }
 template <typename T, int DEPTH>
 static cudaError_t launch_fused_d(const FusedParams& p, int num_sms, cudaStream_t s) {
+    if (p.f.g.CE * sizeof(T) == 65536) return launch_fused_ds<T, DEPTH, 3, 65536>(p, num_sms, s);       // IHPR_FUSED_CHUNK=64 (tuning experiments)
     switch (fused_stages()) {
         case 3: return launch_fused_ds<T, DEPTH, 3>(p, num_sms, s);
         case 4: return launch_fused_ds<T, DEPTH, 4>(p, num_sms, s);
