@@ -462,7 +462,11 @@ class _DeconvBnReluTrain(torch.autograd.Function):
         Cout = weight.shape[1]
         dev = x.device
         xb = _nhwc_bf16(x)
-        wb = weight.detach().to(torch.bfloat16).contiguous()
+        if weight.dtype == torch.bfloat16 and weight.is_contiguous():
+            wb = weight.detach()
+        else:           # cast and re-layout (a channels_last parameter) in ONE copy kernel
+            wb = torch.empty(weight.shape, dtype=torch.bfloat16, device=dev)
+            wb.copy_(weight.detach())
         g = gamma.detach().to(torch.float32).contiguous()
         b_ = beta.detach().to(torch.float32).contiguous()
         for t, n in ((running_mean, "running_mean"), (running_var, "running_var")):
