@@ -64,6 +64,7 @@ CASES = [
     (5, 16, 16),        # the head's second block: 16 x 16 -> 32 x 32
     (10, 32, 32),       # 160 forward items on 148 SMs: the last wave runs as half items; CTAs own several items
     (40, 32, 32),       # 160 input-gradient items: half items in the kDgrad mode too
+    (2, 32, 16),        # 16 wide, 32 high: two 16-row groups per sample
 ]
 
 
