@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/k5_experiments.sh -- K5 (one-launch forward + backward): what the exchange and the L2 policies cost.  Uses a library built with
-# -DIHPR_TIMING_EXPERIMENTS (build/lib_exp, built in the container); IHPR_DEBUG_NOXCHG bits: 1 = no exchange (WRONG results), 2 = pass 1 without
+# -DIHPR_TIMING_EXPERIMENTS (build/lib_exp: tools/build_experiment_lib.sh, run in the container); IHPR_DEBUG_NOXCHG bits: 1 = no exchange (WRONG results), 2 = pass 1 without
 # evict_last, 4 = pass 2 without evict_first.  Times from tools/kbench.cu (20 launches), DRAM bytes from ncu.
 mkdir -p gpurun_out/k5x build
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/kbench tools/kbench.cu -L"integral-human-pose-regression-for-3d-human-pose-estimation_b200/lib" -lihpr_b200 -Xlinker -rpath -Xlinker "$PWD/integral-human-pose-regression-for-3d-human-pose-estimation_b200/lib" 2>&1 | tail -2
