@@ -72,7 +72,9 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 // Clusters (CS = 2 or 4 CTAs): the CTAs of a cluster are consecutive taps of ONE phase on the same pixel range, so their A operand (the gradient
 // tile, half of the operand stream) is the same: each CTA loads 1 / CS of its four 64-channel boxes and TMA-multicasts them into all CS shared
 // memories; a stage is refilled only when the MMA issuers of all CS CTAs have released it (tcgen05.commit multicast onto every `empty` barrier).
-// L2 -> SM traffic per call: 537 MB (CS = 1), 403 MB (CS = 2), 336 MB (CS = 4) at B = 32.
+// L2 -> SM traffic per call: 537 MB (CS = 1), 403 MB (CS = 2), 336 MB (CS = 4) at B = 32.  Measured on B200 (profiles/r02_k11_wgrad_bench.txt): parity-green and
+// NOT faster (50.4 us alone, 52.1 us in pairs, ~84 us in fours; 32-pixel stages in a 6-deep ring 58.8 us) -- the kernel runs at 80 % of the MMA rate and is
+// not bound by that stream, so the default is CS = 1 with 64-pixel stages; the cluster / fine-stage forms stay as opt-in variants.
 //   map_x : input, 4-D {C, Win, Hin, B} bf16 NHWC, box {64, Win, 64 / Win, 1}, zero fill out of bounds
 //   map_dy: output gradient, 5-D phase view {2 C (px, c), Win, 2 (py), Hin, B}, box {64, Win, 1, 64 / Win, 1}
 template <int CS, int BKP>
