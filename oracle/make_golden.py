@@ -195,6 +195,67 @@ def make_aug_goldens():
         print(f"{name:34s} {os.path.getsize(path)/1024:.1f} KiB")
 
 
+DECONV_CASES = (("deconv_block_train_b2_h16w16", 41, 2, 16, 16), ("deconv_block_train_b1_h8w32", 42, 1, 8, 32))
+
+
+def make_deconv_goldens():
+    """Row N1 (training side): the third block of the reference's own HeadNet.deconv_layers (main/model.py:22-38,
+    ConvTranspose2d(256, 256, k4 s2 p1) + BatchNorm2d + ReLU) run in TRAINING mode in fp64 on seeded inputs, forward and autograd
+    backward; the numpy restatement oracle/deconv_block_ref.py is asserted against it while the fixture is written.  The fixture keeps
+    the seed (inputs are regenerated by deconv_block_ref.problem), the per-channel quantities in full and strided samples of the big tensors."""
+    import torch
+    import torchvision.models.resnet as tvr
+    from oracle import deconv_block_ref as R
+    if not hasattr(tvr, "model_zoo"):
+        tvr.model_zoo, tvr.model_urls = None, {}
+    ref = Reference()
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ref.tmp, "ref", "main"))
+    try:
+        import model as ref_model
+    finally:
+        os.chdir(cwd)
+    ref.cfg.depth_dim = 64
+    head = ref_model.HeadNet(18).double()
+    block = head.deconv_layers[6:9]                      # ConvTranspose2d(256, 256), BatchNorm2d(256), ReLU
+    conv, bn = block[0], block[1]
+    assert isinstance(conv, torch.nn.ConvTranspose2d) and conv.in_channels == 256 and conv.out_channels == 256 and isinstance(bn, torch.nn.BatchNorm2d)
+    for name, seed, B, H, W in DECONV_CASES:
+        x, w, gamma, beta, rm, rv, dout = R.problem(seed, B, 256, 256, H, W)
+        with torch.no_grad():
+            conv.weight.copy_(torch.from_numpy(w))
+            bn.weight.copy_(torch.from_numpy(gamma))
+            bn.bias.copy_(torch.from_numpy(beta))
+            bn.running_mean.copy_(torch.from_numpy(rm))
+            bn.running_var.copy_(torch.from_numpy(rv))
+        block.train()
+        for p_ in block.parameters():
+            p_.grad = None
+        xt = torch.from_numpy(x).requires_grad_(True)
+        out = block(xt)
+        out.backward(torch.from_numpy(dout))
+        got = {"out": out.detach().numpy(), "dx": xt.grad.numpy(), "dw": conv.weight.grad.numpy(), "dgamma": bn.weight.grad.numpy(),
+               "dbeta": bn.bias.grad.numpy(), "running_mean": bn.running_mean.numpy().copy(), "running_var": bn.running_var.numpy().copy()}
+        block.eval()
+        with torch.no_grad():
+            got["out_eval"] = block(torch.from_numpy(x)).numpy()       # with the UPDATED running statistics
+        # the numpy restatement against the reference's modules
+        f = R.forward_train(x, w, gamma, beta, rm, rv)
+        b = R.backward_train(x, w, gamma, beta, dout)
+        e = R.forward_eval(x, w, gamma, beta, f["running_mean"], f["running_var"])
+        for key, val in (("out", f["out"]), ("running_mean", f["running_mean"]), ("running_var", f["running_var"]), ("dx", b["dx"]), ("dw", b["dw"]),
+                         ("dgamma", b["dgamma"]), ("dbeta", b["dbeta"]), ("out_eval", e)):
+            err = np.abs(val - got[key]).max() / max(np.abs(got[key]).max(), 1e-30)
+            assert err <= 1e-10, (name, key, err)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, seed=seed, shape=np.array([B, 256, 256, H, W]), mean=f["mean"], var=f["var"],
+                            running_mean=got["running_mean"], running_var=got["running_var"], dgamma=got["dgamma"], dbeta=got["dbeta"],
+                            out_sub=got["out"][:, ::8, ::4, ::4], out_eval_sub=got["out_eval"][:, ::8, ::4, ::4], dx_sub=got["dx"][:, ::8, ::2, ::2],
+                            dw_sub=got["dw"][::16, ::16], out_sum=got["out"].sum(axis=(0, 2, 3)), dx_sum=got["dx"].sum(axis=(0, 2, 3)),
+                            dw_tapsum=got["dw"].sum(axis=(0, 1)))
+        print(f"{name:34s} {os.path.getsize(path)/1024:.1f} KiB")
+
+
 def dump_reference_state_keys():
     """state_dict keys + shapes of the reference's own get_pose_net (main/model.py:105-114) for ResNet-50 / J=18,
     as a fixture for the checkpoint-compatibility test of ihpr_b200.model (the reference's resnet.py imports
@@ -225,8 +286,12 @@ if __name__ == "__main__":
     if "--aug" in sys.argv:                  # only the augmentation fixtures
         make_aug_goldens()
         sys.exit(0)
+    if "--deconv" in sys.argv:               # only the deconv-block fixtures (row N1, training side)
+        make_deconv_goldens()
+        sys.exit(0)
     if "--keys" not in sys.argv:
         main()
         make_post_goldens()
         make_aug_goldens()
+        make_deconv_goldens()
     dump_reference_state_keys()

@@ -17,7 +17,7 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("post_", "aug_")))
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("post_", "aug_", "deconv_")))
 
 
 def post_golden_names():
@@ -47,6 +47,14 @@ def load_post_golden(name):
         g[k] = int(g[k])
     g.setdefault("flipped", None)
     return g
+
+
+def deconv_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "deconv_*.npz")))
+
+
+def load_deconv_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 
 
 def load_golden(name):

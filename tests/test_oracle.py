@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, load_post_golden, post_golden_names
+from conftest import deconv_golden_names, golden_names, load_deconv_golden, load_golden, load_post_golden, post_golden_names
 from oracle import coords_post_ref, inputs, truth
 from oracle.soft_argmax_ref import RefJointLocationLoss, ref_fwd_bwd, ref_soft_argmax
 
@@ -181,3 +181,51 @@ def test_augment_oracle_matches_reference_golden(name):
         assert np.array_equal(o_img.reshape(-1)[::97], g["img_sub"][n])
         assert np.abs(o_trans - g["trans"][n]).max() <= 1e-9
         assert np.abs(o_joint - g["joint"][n]).max() <= 1e-4 and np.array_equal(o_vis, g["vis"][n])
+
+
+@pytest.mark.parametrize("name", deconv_golden_names())
+def test_deconv_block_oracle_matches_reference_golden(name):
+    """oracle/deconv_block_ref.py (numpy fp64) against the fixture written from the reference's OWN HeadNet block (main/model.py:22-38,
+    run in training mode in fp64 by oracle/make_golden.py --deconv): output, running statistics, every gradient."""
+    from oracle import deconv_block_ref as R
+    g = load_deconv_golden(name)
+    B, Cin, Cout, H, W = (int(v) for v in g["shape"])
+    x, w, gamma, beta, rm, rv, dout = R.problem(int(g["seed"]), B, Cin, Cout, H, W)
+    f = R.forward_train(x, w, gamma, beta, rm, rv)
+    b = R.backward_train(x, w, gamma, beta, dout)
+    e = R.forward_eval(x, w, gamma, beta, f["running_mean"], f["running_var"])
+    pairs = (("running_mean", f["running_mean"]), ("running_var", f["running_var"]), ("dgamma", b["dgamma"]), ("dbeta", b["dbeta"]),
+             ("out_sub", f["out"][:, ::8, ::4, ::4]), ("out_eval_sub", e[:, ::8, ::4, ::4]), ("dx_sub", b["dx"][:, ::8, ::2, ::2]),
+             ("dw_sub", b["dw"][::16, ::16]), ("out_sum", f["out"].sum(axis=(0, 2, 3))), ("dx_sum", b["dx"].sum(axis=(0, 2, 3))),
+             ("dw_tapsum", b["dw"].sum(axis=(0, 1))), ("mean", f["mean"]), ("var", f["var"]))
+    for key, val in pairs:
+        assert np.abs(val - g[key]).max() <= 1e-9 * max(np.abs(g[key]).max(), 1e-30), key
+
+
+def test_deconv_block_oracle_known_answers():
+    """a single input pixel spreads the 4 x 4 kernel over output rows / columns 2 i - 1 ... 2 i + 2 (torch.nn.ConvTranspose2d, stride 2,
+    padding 1), clipped at the border; the gradients of a linear functional are the transposes of that map."""
+    from oracle import deconv_block_ref as R
+    x = np.zeros((1, 2, 3, 3))
+    w = np.arange(2 * 3 * 16, dtype=np.float64).reshape(2, 3, 4, 4)
+    x[0, 1, 1, 1] = 1.0
+    y = R.conv_transpose2d(x, w)
+    assert y.shape == (1, 3, 6, 6)
+    assert np.array_equal(y[0, :, 1:5, 1:5], w[1]) and y.sum() == w[1].sum()
+    x[:] = 0
+    x[0, 0, 0, 0] = 1.0                               # top-left corner: kernel rows / columns 0 fall outside
+    y = R.conv_transpose2d(x, w)
+    assert np.array_equal(y[0, :, 0:3, 0:3], w[0][:, 1:, 1:]) and y[0, :, 3:, :].sum() == 0
+    r = np.random.RandomState(0)
+    x, w = r.randn(2, 3, 4, 5), r.randn(3, 2, 4, 4)
+    gamma, beta, dout = r.rand(2) + 0.5, r.randn(2), r.randn(2, 2, 8, 10)
+    b = R.backward_train(x, w, gamma, beta, dout)
+    # finite differences of sum(out * dout) in x and w
+    f0 = (R.forward_train(x, w, gamma, beta)["out"] * dout).sum()
+    for arr, grad in ((x, b["dx"]), (w, b["dw"])):
+        for idx in ((0, 0, 0, 0), (1, 1, 2, 3), (1, 0, 3, 1)):
+            old = arr[idx]
+            arr[idx] = old + 1e-6
+            f1 = (R.forward_train(x, w, gamma, beta)["out"] * dout).sum()
+            arr[idx] = old
+            assert abs((f1 - f0) / 1e-6 - grad[idx]) <= 1e-4 * max(1.0, abs(grad[idx])), (idx, (f1 - f0) / 1e-6, grad[idx])
