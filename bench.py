@@ -662,6 +662,19 @@ def train_record(args, dev, world, rank):
                              "roofline_frac": g["roofline"]["frac"], "e2e_value": g["e2e"]["value"]}
     except Exception as e:      # noqa: the eager record stands on its own
         rec["cuda_graph"] = {"error": repr(e)[:300]}
+    if world == 1:
+        # row N1's effect in the driver's own record: the same graphed step with deconv blocks 2 / 3 left to cuDNN + torch BatchNorm
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            a2 = argparse.Namespace(**vars(a))
+            a2.stock_deconv = True
+            s_ = train_core(a2, dev, world, rank, resnet=50, fused_head=True, crit_kind="head", cuda_graph=True,
+                            steps=args.train_steps, warmup=5)
+            rec["cuda_graph_stock_deconv"] = {"value": s_["value"], "unit": s_["unit"], "ms_per_step": s_["ms_per_step"],
+                                              "note": "comparison arm: --stock-deconv (the head's deconv blocks 2 / 3 on cuDNN + nn.BatchNorm2d instead of K9 / K10 / K11)"}
+        except Exception as e:      # noqa
+            rec["cuda_graph_stock_deconv"] = {"error": repr(e)[:300]}
     g = rec["cuda_graph"]
     rec["best"] = ({"launch": "cuda_graph", "value": g["value"], "ms_per_step": g["ms_per_step"]} if g.get("value", 0) > rec["value"]
                    else {"launch": "eager", "value": rec["value"], "ms_per_step": rec["ms_per_step"]})
